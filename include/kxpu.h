@@ -1,0 +1,231 @@
+/*
+ * kxpu.h -- C ABI of libkxpu.so: the B200-native (sm_100a) implementation of the
+ * kata-xpu-device-plugin discovery hot path.
+ *
+ * The reference (Apokleos/kata-xpu-device-plugin) is one Go binary with no FFI of its
+ * own; this header is the boundary a cgo shim binds.  Every entry
+ * point names the reference code it replaces (file:line, paths relative to the
+ * reference repository root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.
+ *   - every function returns an int32 status: KXPU_OK (0) or a negative KXPU_E_* code.
+ *   - inputs are borrowed for the duration of the call (cgo rule: no Go pointer is
+ *     retained); outputs are caller-allocated, `cap` is passed, and when `cap` is too
+ *     small the call returns KXPU_E_NOSPACE after storing the required size.
+ *   - opaque handles (kxpu_ctx, kxpu_table) are owned by the library.
+ *   - there is NO CPU fallback: without a usable sm_100 GPU kxpu_ctx_create fails with
+ *     KXPU_E_NOGPU and nothing else can be called.
+ *   - a kxpu_ctx may be used from several OS threads; calls on one ctx are serialised
+ *     by an internal mutex (grpc-go runs Allocate handlers concurrently,
+ *     pkg/device_plugin/generic_device_plugin.go:320).
+ */
+#ifndef KXPU_H
+#define KXPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KXPU_ABI_VERSION 1
+
+/* status codes */
+#define KXPU_OK             0
+#define KXPU_E_INVALID     -1  /* bad argument */
+#define KXPU_E_CUDA        -2  /* CUDA runtime/driver error (see kxpu_last_error) */
+#define KXPU_E_NOGPU       -3  /* no CUDA device / not an sm_100 part */
+#define KXPU_E_NOSPACE     -4  /* caller buffer too small; required size was stored */
+#define KXPU_E_CAPACITY    -5  /* internal table capacity exceeded after growth limit */
+#define KXPU_E_NCCL        -6  /* NCCL missing or failed */
+#define KXPU_E_UNSUPPORTED -7  /* input outside the supported domain (documented per call) */
+#define KXPU_E_NOMEM       -8
+
+#define KXPU_ROW_MISS  (-1)            /* kxpu_lookup: key not present (reference: "") */
+#define KXPU_REJECTED  0xFFFFFFFFu     /* kxpu_classify: record not accepted */
+
+typedef struct kxpu_ctx   kxpu_ctx;
+typedef struct kxpu_table kxpu_table;
+
+/* ------------------------------------------------------------------ context */
+
+/* Bind to one GPU (ordinal as in CUDA_VISIBLE_DEVICES order).  Fails with
+ * KXPU_E_NOGPU when there is no device or its compute capability major is not 10. */
+int32_t kxpu_ctx_create(int32_t gpu_ordinal, kxpu_ctx **out);
+int32_t kxpu_ctx_destroy(kxpu_ctx *ctx);
+const char *kxpu_strerror(int32_t status);
+/* Detailed message of the last failing call on this ctx (static storage inside ctx). */
+const char *kxpu_last_error(kxpu_ctx *ctx);
+/* Number of kernel launches issued by this ctx so far (bench accounting). */
+uint64_t kxpu_launch_count(kxpu_ctx *ctx);
+/* Device time in ms of the most recent call's kernels, per stage (parse, finalize,
+ * lookup, ...).  Index with KXPU_T_*.  Measured with CUDA events on the ctx stream. */
+#define KXPU_T_PARSE    0
+#define KXPU_T_FINALIZE 1
+#define KXPU_T_LOOKUP   2
+#define KXPU_T_NAMES    3
+#define KXPU_T_CLASSIFY 4
+#define KXPU_T_EMIT     5
+#define KXPU_T_MERGE    6
+#define KXPU_T_COUNT    8
+int32_t kxpu_last_timings(kxpu_ctx *ctx, float ms_out[KXPU_T_COUNT]);
+
+/* Device / pinned memory helpers so a host program without a CUDA binding can keep
+ * inputs resident (used by bench.py for the HBM-resident `value` measurement and for
+ * pinned staging buffers of the `e2e` measurement). */
+int32_t kxpu_dev_alloc(kxpu_ctx *ctx, size_t bytes, void **d_out);
+int32_t kxpu_dev_free(kxpu_ctx *ctx, void *d_ptr);
+int32_t kxpu_dev_upload(kxpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int32_t kxpu_dev_download(kxpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+/* d_dst[i*n .. (i+1)*n) = d_src[0..n) for i in [0,copies): builds the "pci.ids x1000"
+ * text of BASELINE.json configs[3] on the device. */
+int32_t kxpu_dev_replicate(kxpu_ctx *ctx, void *d_dst, const void *d_src, size_t n, size_t copies);
+int32_t kxpu_pinned_alloc(kxpu_ctx *ctx, size_t bytes, void **h_out);
+int32_t kxpu_pinned_free(kxpu_ctx *ctx, void *h_ptr);
+int32_t kxpu_sync(kxpu_ctx *ctx);
+
+/* ----------------------------------------------- S2: pci.ids parse + lookup */
+
+/* Parse a pci.ids text once and build the (vendor,device) -> row table.
+ * Replaces the per-call file scan of getDeviceName/locateVendor
+ * (pkg/device_plugin/device_plugin.go:208-275): for every key the table answers
+ * exactly what that scan would answer on the same text --
+ *   - the vendor anchor is the FIRST line whose first four bytes equal the vendor id
+ *     (device_plugin.go:263-267),
+ *   - its block is the run of following lines that start with '#' or '\t'
+ *     (device_plugin.go:229-236); the first block line starting with "\t"+device wins
+ *     (device_plugin.go:237),
+ *   - bufio.Scanner semantics: a line of >= 65536 bytes ends the scan
+ *     (device_plugin.go:262, bufio.MaxScanTokenSize).
+ * Keys are (vendor<<16)|device rendered as four lowercase hex digits each, which is
+ * what sysfs provides (device_plugin.go:142,164).
+ * `text` is host memory; it is copied to the GPU inside the call and may be freed
+ * afterwards (the table keeps sanitised names, not the text). */
+int32_t kxpu_pciids_load(kxpu_ctx *ctx, const uint8_t *text, size_t n, kxpu_table **out);
+/* Same, text already resident in device memory (16-byte aligned pointer). */
+int32_t kxpu_pciids_load_device(kxpu_ctx *ctx, const void *d_text, size_t n, kxpu_table **out);
+int32_t kxpu_table_free(kxpu_ctx *ctx, kxpu_table *t);
+/* Number of (vendor,device) rows that a lookup can hit. */
+int32_t kxpu_table_rows(kxpu_ctx *ctx, kxpu_table *t, uint32_t *n_rows);
+/* Dump the table in file order (ascending line offset).  Arrays hold `cap` entries;
+ * on KXPU_E_NOSPACE *n_rows holds the required count. */
+int32_t kxpu_table_export(kxpu_ctx *ctx, kxpu_table *t, uint32_t *keys, uint64_t *line_off,
+                          int32_t *rows, size_t cap, uint32_t *n_rows);
+
+/* Batched join: rows_out[i] = row handle of keys[i] or KXPU_ROW_MISS.
+ * Replaces one getDeviceName call per key (device_plugin.go:99). */
+int32_t kxpu_lookup(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *keys, size_t n,
+                    int32_t *rows_out);
+int32_t kxpu_lookup_device(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *d_keys, size_t n,
+                           int32_t *d_rows_out);
+
+/* Sanitised resource names for row handles (device_plugin.go:241-251: TrimPrefix,
+ * TrimSpace, ToUpper, '/'->'_', '.'->'_', \s+ -> '_', strip [^a-zA-Z0-9_.]).
+ * Name i occupies out[offsets[i] .. offsets[i+1]); a miss row yields an empty name
+ * (reference returns "" and the caller falls back to the raw id, :100-103).
+ * *need receives the total bytes required. */
+int32_t kxpu_names(kxpu_ctx *ctx, kxpu_table *t, const int32_t *rows, size_t n,
+                   uint8_t *out, size_t cap, uint32_t *offsets, size_t *need);
+
+/* ------------------------------------------------- multi-GPU (one rank/GPU) */
+
+/* NCCL is loaded lazily (dlopen libnccl.so.2); single-GPU users never need it. */
+#define KXPU_COMM_ID_BYTES 128
+int32_t kxpu_comm_unique_id(uint8_t id_out[KXPU_COMM_ID_BYTES]);
+int32_t kxpu_comm_init(kxpu_ctx *ctx, int32_t nranks, int32_t rank,
+                       const uint8_t id[KXPU_COMM_ID_BYTES]);
+int32_t kxpu_comm_destroy(kxpu_ctx *ctx);
+/* Collective.  Each rank passes its shard of one logical text: bytes
+ * [global_base, global_base+n), cut where a top-level line (first byte neither '\t'
+ * nor '#') starts, i.e. at a vendor-id boundary.  Every rank parses its shard,
+ * the hit rows (key, line offset, anchor offset, sanitised name) are exchanged with
+ * ONE ncclAllGather and min-merged, and every rank returns the same table, equal to
+ * kxpu_pciids_load on the concatenated text. */
+int32_t kxpu_pciids_load_sharded(kxpu_ctx *ctx, const void *d_text_shard, size_t n,
+                                 uint64_t global_base, kxpu_table **out);
+
+/* ----------------------------------------------- S1/S4: discovery classify */
+
+/* One sysfs entry under /sys/bus/pci/devices, raw bytes as the Go host gathered them
+ * (readIDFromFile / readLink, device_plugin.go:183-202), in filepath.Walk order
+ * (device_plugin.go:132).  64 bytes. */
+typedef struct kxpu_devrec {
+    char     bdf[16];        /* entry name (info.Name()), NUL padded, <= 15 bytes      */
+    uint8_t  vendor_txt[8];  /* first 8 bytes of the `vendor` file, e.g. "0x10de\n"     */
+    uint8_t  device_txt[8];  /* first 8 bytes of the `device` file                      */
+    char     driver[16];     /* basename of the `driver` link, NUL padded               */
+    uint32_t iommu_group;    /* basename of the `iommu_group` link, decimal             */
+    uint8_t  vendor_len;     /* length of the vendor file (0..8; longer => set flag)    */
+    uint8_t  device_len;
+    uint8_t  flags;          /* KXPU_REC_* */
+    uint8_t  reserved0;
+    uint32_t reserved1[2];
+} kxpu_devrec;
+
+#define KXPU_REC_VENDOR_ERR 0x01u /* readIDFromFile(vendor) failed  (device_plugin.go:143) */
+#define KXPU_REC_DRIVER_ERR 0x02u /* readLink(driver) failed        (device_plugin.go:152) */
+#define KXPU_REC_IOMMU_ERR  0x04u /* readLink(iommu_group) failed   (device_plugin.go:158) */
+#define KXPU_REC_DEVICE_ERR 0x08u /* readIDFromFile(device) failed  (device_plugin.go:165) */
+#define KXPU_REC_IS_DIR     0x10u /* info.IsDir()                   (device_plugin.go:137) */
+
+/* Caller-allocated outputs of kxpu_classify; every array has room for n entries
+ * (group_off / dev_off: n+1). */
+typedef struct kxpu_classify_out {
+    uint32_t *accept_index;  /* [n] busIndex of record i, or KXPU_REJECTED               */
+    /* iommuMap (device_plugin.go:31,171): groups in first-seen walk order               */
+    uint32_t *group_ids;     /* [n_groups]                                                */
+    uint32_t *group_off;     /* [n_groups+1] into group_members                           */
+    uint32_t *group_members; /* [n_accepted] record indices, walk order inside a group    */
+    /* deviceMap (device_plugin.go:34,169): device ids in first-seen walk order; each
+     * lists the groups whose FIRST member has that device id, in first-seen order.
+     * dev_ids holds the id string bytes (little-endian packed, NUL padded, <= 8).       */
+    uint64_t *dev_ids;       /* [n_devids]                                                */
+    uint32_t *dev_off;       /* [n_devids+1] into dev_groups                              */
+    uint32_t *dev_groups;    /* [n_groups] group ids == pluginapi.Device.ID (:94)         */
+    uint32_t  n_accepted;
+    uint32_t  n_groups;
+    uint32_t  n_devids;
+} kxpu_classify_out;
+
+/* createIommuDeviceMap (device_plugin.go:126-180) + the device-list build of
+ * createDevicePlugins (device_plugin.go:91-98) over a flat record table. */
+int32_t kxpu_classify(kxpu_ctx *ctx, const kxpu_devrec *recs, size_t n, kxpu_classify_out *out);
+
+/* ------------------------------------------------------- S3: CDI spec emit */
+
+/* One accepted device as generateCDISpec sees it (device_plugin.go:59-76). 32 bytes. */
+typedef struct kxpu_cdidev {
+    char     bdf[16];       /* dev.addr, NUL padded                                       */
+    uint32_t iommu_group;   /* devName (decimal)                                          */
+    uint32_t reserved;
+    uint64_t index;         /* dev.index                                                  */
+} kxpu_cdidev;
+
+#define KXPU_FMT_YAML 0  /* yaml.v3 encoder, SetIndent(2)   (cdi/spec.go:104-112)          */
+#define KXPU_FMT_JSON 1  /* json.MarshalIndent(spec,"","  ") (cdi/spec.go:114-123)         */
+
+/* generateCDISpec + CdiSpec.Save (device_plugin.go:55-80, cdi/spec.go:85-127) into a
+ * caller buffer; devices are emitted in array order (canonical order: ascending index).
+ * Call with out==NULL/cap==0 to obtain *len.  The host writes the file. */
+int32_t kxpu_cdi_emit(kxpu_ctx *ctx, int32_t format, const kxpu_cdidev *devs, size_t n,
+                      uint8_t *out, size_t cap, size_t *len);
+
+/* ------------------------------------------------------ S5: Allocate names */
+
+/* updateResponseForCDI / QualifiedName (generic_device_plugin.go:274-299,
+ * cdi/cdi-utils.go:9): name i = "nvidia.com/gpu=" + decimal(idx[i]). */
+int32_t kxpu_alloc_names(kxpu_ctx *ctx, const uint64_t *idx, size_t n, uint8_t *out,
+                         size_t cap, uint32_t *offsets, size_t *need);
+
+/* ListAndWatchResponse wire bytes for a device list (generic_device_plugin.go:224):
+ * repeated field 1 { string ID = 1 (decimal group); string health = 2 }.
+ * healthy[i] != 0 -> "Healthy" else "Unhealthy"; healthy == NULL -> all healthy. */
+int32_t kxpu_lw_encode(kxpu_ctx *ctx, const uint32_t *group_ids, const uint8_t *healthy,
+                       size_t n, uint8_t *out, size_t cap, size_t *len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KXPU_H */

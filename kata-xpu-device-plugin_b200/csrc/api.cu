@@ -1,0 +1,468 @@
+// api.cu -- context, memory helpers and the pci.ids entry points of the C ABI (include/kxpu.h).
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "pciids.cu"  // kernels (single translation unit keeps them inlinable and static)
+
+struct kxpu_table {
+    uint32_t cap = 0, shift = 0;
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    KxTableDev dev{};
+    unsigned long long *tile_state = nullptr;
+    int32_t *row_of_slot = nullptr;
+    uint32_t *row_key = nullptr;
+    unsigned long long *row_line = nullptr;
+    unsigned long long *row_anchor = nullptr;
+    uint32_t *row_name_off = nullptr;
+    uint32_t *row_name_len = nullptr;
+    uint8_t *blob = nullptr;
+    uint32_t blob_cap = 0;
+    uint32_t n_rows = 0;
+    uint32_t blob_used = 0;
+    void *gather = nullptr;  // sharded load: all-gathered row slabs (names live here)
+};
+
+static const char *kx_err_names[] = {
+    "ok", "invalid argument", "CUDA error", "no sm_100 GPU available", "output buffer too small",
+    "table capacity exceeded", "NCCL unavailable or failed", "input outside the supported domain", "out of memory"};
+
+extern "C" const char *kxpu_strerror(int32_t status) {
+    int i = -status;
+    if (i < 0 || i > 8) return "unknown status";
+    return kx_err_names[i];
+}
+
+extern "C" const char *kxpu_last_error(kxpu_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+extern "C" uint64_t kxpu_launch_count(kxpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int32_t kxpu_ctx_create(int32_t ordinal, kxpu_ctx **out) {
+    if (!out) return KXPU_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || ordinal < 0 || ordinal >= count) {
+        cudaGetLastError();
+        return KXPU_E_NOGPU;  // no CPU fallback: the caller must treat this as fatal
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ordinal) != cudaSuccess) return KXPU_E_NOGPU;
+    if (prop.major != 10) return KXPU_E_NOGPU;  // kernels are built for sm_100a only
+    kxpu_ctx *c = new (std::nothrow) kxpu_ctx();
+    if (!c) return KXPU_E_NOMEM;
+    c->device = ordinal;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return KXPU_E_CUDA;
+    }
+    for (int i = 0; i < 2 * KXPU_T_COUNT; i++) cudaEventCreate(&c->ev[i]);
+    cudaMallocHost((void **)&c->h_ctl, 64 * sizeof(uint32_t));
+    // keep stream-ordered allocations cached: table builds allocate/free per call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ordinal) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaFuncSetAttribute(kxparse::parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(kxparse::ParseSmem));
+    *out = c;
+    return KXPU_OK;
+}
+
+extern "C" int32_t kxpu_ctx_destroy(kxpu_ctx *ctx) {
+    if (!ctx) return KXPU_E_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2 * KXPU_T_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaFreeHost(ctx->h_ctl);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return KXPU_OK;
+}
+
+extern "C" int32_t kxpu_last_timings(kxpu_ctx *ctx, float ms_out[KXPU_T_COUNT]) {
+    if (!ctx || !ms_out) return KXPU_E_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < KXPU_T_COUNT; i++) {
+        ms_out[i] = 0.f;
+        if (ctx->ev_used[i]) cudaEventElapsedTime(&ms_out[i], ctx->ev[2 * i], ctx->ev[2 * i + 1]);
+    }
+    return KXPU_OK;
+}
+
+// ------------------------------------------------------------------ memory helpers
+#define KX_ENTER(ctx)                          \
+    if (!(ctx)) return KXPU_E_INVALID;         \
+    std::lock_guard<std::mutex> guard__((ctx)->mu); \
+    cudaSetDevice((ctx)->device)
+
+extern "C" int32_t kxpu_dev_alloc(kxpu_ctx *ctx, size_t bytes, void **d_out) {
+    KX_ENTER(ctx);
+    if (!d_out) return KXPU_E_INVALID;
+    KX_CUDA(ctx, cudaMalloc(d_out, bytes ? bytes : 16));
+    return KXPU_OK;
+}
+extern "C" int32_t kxpu_dev_free(kxpu_ctx *ctx, void *d_ptr) {
+    KX_ENTER(ctx);
+    KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KX_CUDA(ctx, cudaFree(d_ptr));
+    return KXPU_OK;
+}
+extern "C" int32_t kxpu_dev_upload(kxpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    KX_ENTER(ctx);
+    KX_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KXPU_OK;
+}
+extern "C" int32_t kxpu_dev_download(kxpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+    KX_ENTER(ctx);
+    KX_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KXPU_OK;
+}
+extern "C" int32_t kxpu_dev_replicate(kxpu_ctx *ctx, void *d_dst, const void *d_src, size_t n, size_t copies) {
+    KX_ENTER(ctx);
+    // doubling copy: log2(copies) device-to-device memcpys
+    if (copies == 0 || n == 0) return KXPU_OK;
+    uint8_t *dst = (uint8_t *)d_dst;
+    if (dst != d_src) KX_CUDA(ctx, cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToDevice, ctx->stream));
+    size_t have = 1;
+    while (have < copies) {
+        size_t add = std::min(have, copies - have);
+        KX_CUDA(ctx, cudaMemcpyAsync(dst + have * n, dst, add * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        have += add;
+    }
+    KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KXPU_OK;
+}
+extern "C" int32_t kxpu_pinned_alloc(kxpu_ctx *ctx, size_t bytes, void **h_out) {
+    KX_ENTER(ctx);
+    if (!h_out) return KXPU_E_INVALID;
+    KX_CUDA(ctx, cudaMallocHost(h_out, bytes ? bytes : 16));
+    return KXPU_OK;
+}
+extern "C" int32_t kxpu_pinned_free(kxpu_ctx *ctx, void *h_ptr) {
+    KX_ENTER(ctx);
+    KX_CUDA(ctx, cudaFreeHost(h_ptr));
+    return KXPU_OK;
+}
+extern "C" int32_t kxpu_sync(kxpu_ctx *ctx) {
+    KX_ENTER(ctx);
+    KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KXPU_OK;
+}
+
+// ------------------------------------------------------------------ table build
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static void table_release(kxpu_ctx *ctx, kxpu_table *t) {
+    if (!t) return;
+    if (t->arena) cudaFreeAsync(t->arena, ctx->stream);
+    if (t->gather) cudaFreeAsync(t->gather, ctx->stream);
+    delete t;
+}
+
+static int32_t table_alloc(kxpu_ctx *ctx, uint32_t cap, uint32_t blob_cap, uint32_t num_tiles, kxpu_table **out) {
+    kxpu_table *t = new (std::nothrow) kxpu_table();
+    if (!t) return KXPU_E_NOMEM;
+    t->cap = cap;
+    uint32_t lg = 0;
+    while ((1u << lg) < cap) lg++;
+    t->shift = 32 - lg;
+    const size_t slots = (size_t)cap + 1;
+    size_t off = 0;
+    // 0xff-initialised region first (one memset), then the zero-initialised region
+    size_t o_keys = off;        off = align_up(off + slots * 4, 256);
+    size_t o_min_line = off;    off = align_up(off + slots * 8, 256);
+    size_t o_min_anchor = off;  off = align_up(off + slots * 8, 256);
+    size_t o_vfirst = off;      off = align_up(off + 65536 * 8, 256);
+    size_t o_trunc = off;       off = align_up(off + 8, 256);
+    size_t ff_bytes = off;
+    size_t o_counters = off;    off = align_up(off + KX_C_COUNT * 4, 256);
+    size_t o_tiles = off;       off = align_up(off + (size_t)num_tiles * 8, 256);
+    size_t zero_bytes = off - ff_bytes;
+    size_t o_row_of_slot = off; off = align_up(off + slots * 4, 256);
+    size_t o_row_key = off;     off = align_up(off + slots * 4, 256);
+    size_t o_row_line = off;    off = align_up(off + slots * 8, 256);
+    size_t o_row_anchor = off;  off = align_up(off + slots * 8, 256);
+    size_t o_row_noff = off;    off = align_up(off + slots * 4, 256);
+    size_t o_row_nlen = off;    off = align_up(off + slots * 4, 256);
+    size_t o_blob = off;        off = align_up(off + blob_cap, 256);
+    t->arena_bytes = off;
+    cudaError_t e = cudaMallocAsync(&t->arena, off, ctx->stream);
+    if (e != cudaSuccess) {
+        KX_SET_ERR(ctx, "cudaMallocAsync(%zu) -> %s", off, cudaGetErrorString(e));
+        delete t;
+        return e == cudaErrorMemoryAllocation ? KXPU_E_NOMEM : KXPU_E_CUDA;
+    }
+    uint8_t *b = (uint8_t *)t->arena;
+    t->dev.keys = (uint32_t *)(b + o_keys);
+    t->dev.min_line = (unsigned long long *)(b + o_min_line);
+    t->dev.min_anchor = (unsigned long long *)(b + o_min_anchor);
+    t->dev.vendor_first = (unsigned long long *)(b + o_vfirst);
+    t->dev.trunc = (unsigned long long *)(b + o_trunc);
+    t->dev.counters = (uint32_t *)(b + o_counters);
+    t->dev.cap = cap;
+    t->dev.shift = t->shift;
+    t->dev.max_keys = cap / 2;
+    t->tile_state = (unsigned long long *)(b + o_tiles);
+    t->row_of_slot = (int32_t *)(b + o_row_of_slot);
+    t->row_key = (uint32_t *)(b + o_row_key);
+    t->row_line = (unsigned long long *)(b + o_row_line);
+    t->row_anchor = (unsigned long long *)(b + o_row_anchor);
+    t->row_name_off = (uint32_t *)(b + o_row_noff);
+    t->row_name_len = (uint32_t *)(b + o_row_nlen);
+    t->blob = b + o_blob;
+    t->blob_cap = blob_cap;
+    cudaMemsetAsync(b, 0xff, ff_bytes, ctx->stream);
+    cudaMemsetAsync(b + ff_bytes, 0, zero_bytes, ctx->stream);
+    *out = t;
+    return KXPU_OK;
+}
+
+static int parse_grid(kxpu_ctx *ctx, uint32_t num_tiles) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kxparse::parse_kernel, kxparse::NT,
+                                                  sizeof(kxparse::ParseSmem));
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)per_sm * ctx->sm_count;
+    if (g > (long long)num_tiles) g = num_tiles;
+    return (int)(g < 1 ? 1 : g);
+}
+
+static int32_t launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n,
+                               unsigned long long base, int check_valid) {
+    kxparse::FinalizeParams F;
+    F.text = d_text; F.n = n; F.base = base; F.tab = t->dev;
+    F.row_of_slot = t->row_of_slot; F.row_key = t->row_key; F.row_line = t->row_line; F.row_anchor = t->row_anchor;
+    F.row_name_off = t->row_name_off; F.row_name_len = t->row_name_len;
+    F.blob = t->blob; F.blob_cap = t->blob_cap; F.check_valid = check_valid;
+    unsigned blocks = (t->cap + 1 + kxparse::FIN_WARPS - 1) / kxparse::FIN_WARPS;
+    kxparse::finalize_kernel<<<blocks, kxparse::FIN_WARPS * 32, 0, ctx->stream>>>(F);
+    KX_LAUNCHED(ctx);
+    KX_CUDA(ctx, cudaGetLastError());
+    return KXPU_OK;
+}
+
+// Parse d_text[0..n) (global offsets base..base+n) and finalize.  check_valid=1 yields the
+// final table of a single text; 0 leaves every local candidate row for the sharded merge.
+int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned long long base,
+                       unsigned long long carry_in, int check_valid, kxpu_table **out) {
+    if ((reinterpret_cast<uintptr_t>(d_text) & 15u) != 0) {
+        KX_SET_ERR(ctx, "device text pointer must be 16-byte aligned");
+        return KXPU_E_INVALID;
+    }
+    if (base + n >= (1ull << 44)) return KXPU_E_UNSUPPORTED;
+    const uint32_t num_tiles = (uint32_t)((n + kxparse::T - 1) / kxparse::T);
+    uint32_t cap = 1u << 16;
+    uint32_t blob_cap = (uint32_t)std::min<size_t>(std::max<size_t>(n, 256), 4u << 20);
+    for (int attempt = 0; attempt < 8; attempt++) {
+        kxpu_table *t = nullptr;
+        int32_t rc = table_alloc(ctx, cap, blob_cap, num_tiles, &t);
+        if (rc != KXPU_OK) return rc;
+        if (num_tiles > 0) {
+            KxTimer tm(ctx, KXPU_T_PARSE);
+            kxparse::ParseParams P;
+            P.text = d_text; P.n = n; P.base = base; P.num_tiles = num_tiles;
+            P.tile_state = t->tile_state; P.tab = t->dev; P.carry_in = carry_in;
+            kxparse::parse_kernel<<<parse_grid(ctx, num_tiles), kxparse::NT, sizeof(kxparse::ParseSmem), ctx->stream>>>(P);
+            KX_LAUNCHED(ctx);
+        }
+        {
+            KxTimer tm(ctx, KXPU_T_FINALIZE);
+            rc = launch_finalize(ctx, t, d_text, n, base, check_valid);
+        }
+        if (rc != KXPU_OK) { table_release(ctx, t); return rc; }
+        cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            KX_SET_ERR(ctx, "parse/finalize failed: %s", cudaGetErrorString(e));
+            table_release(ctx, t);
+            return KXPU_E_CUDA;
+        }
+        if (ctx->h_ctl[KX_C_NEED_TRUNC] == 2u) {
+            // a >= 1 KiB stretch without a line start was seen: compute the exact
+            // bufio.ErrTooLong cut-off and finalize again.
+            kxparse::trunc_kernel<<<1, 1024, 0, ctx->stream>>>(d_text, n, base, t->dev.trunc);
+            KX_LAUNCHED(ctx);
+            uint32_t one = 1;
+            cudaMemcpyAsync(&t->dev.counters[KX_C_NEED_TRUNC], &one, 4, cudaMemcpyHostToDevice, ctx->stream);
+            cudaMemsetAsync(&t->dev.counters[KX_C_NROWS], 0, 12, ctx->stream);  // NROWS, BLOB_CURSOR, BLOB_OVERFLOW
+            rc = launch_finalize(ctx, t, d_text, n, base, check_valid);
+            if (rc != KXPU_OK) { table_release(ctx, t); return rc; }
+            cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        if (ctx->h_ctl[KX_C_OVERFLOW]) {
+            table_release(ctx, t);
+            if (cap >= (1u << 28)) return KXPU_E_CAPACITY;
+            cap <<= 2;
+            continue;
+        }
+        if (ctx->h_ctl[KX_C_BLOB_OVERFLOW]) {
+            table_release(ctx, t);
+            if ((size_t)blob_cap >= n) return KXPU_E_CAPACITY;
+            blob_cap = (uint32_t)std::min<size_t>(n, (size_t)blob_cap * 8);
+            continue;
+        }
+        t->n_rows = ctx->h_ctl[KX_C_NROWS];
+        t->blob_used = ctx->h_ctl[KX_C_BLOB_CURSOR];
+        *out = t;
+        return KXPU_OK;
+    }
+    return KXPU_E_CAPACITY;
+}
+
+extern "C" int32_t kxpu_pciids_load_device(kxpu_ctx *ctx, const void *d_text, size_t n, kxpu_table **out) {
+    KX_ENTER(ctx);
+    if (!out || (!d_text && n)) return KXPU_E_INVALID;
+    kx_clear_timings(ctx);
+    return kx_build_table(ctx, (const uint8_t *)d_text, n, 0, 0, 1, out);
+}
+
+extern "C" int32_t kxpu_pciids_load(kxpu_ctx *ctx, const uint8_t *text, size_t n, kxpu_table **out) {
+    KX_ENTER(ctx);
+    if (!out || (!text && n)) return KXPU_E_INVALID;
+    kx_clear_timings(ctx);
+    void *d = nullptr;
+    KX_CUDA(ctx, cudaMallocAsync(&d, n ? n : 16, ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(d, text, n, cudaMemcpyHostToDevice, ctx->stream);
+    int32_t rc = e == cudaSuccess ? kx_build_table(ctx, (const uint8_t *)d, n, 0, 0, 1, out) : KXPU_E_CUDA;
+    if (e != cudaSuccess) KX_SET_ERR(ctx, "H2D copy of the text failed: %s", cudaGetErrorString(e));
+    cudaFreeAsync(d, ctx->stream);
+    return rc;
+}
+
+extern "C" int32_t kxpu_table_free(kxpu_ctx *ctx, kxpu_table *t) {
+    KX_ENTER(ctx);
+    table_release(ctx, t);
+    return KXPU_OK;
+}
+
+extern "C" int32_t kxpu_table_rows(kxpu_ctx *ctx, kxpu_table *t, uint32_t *n_rows) {
+    if (!ctx || !t || !n_rows) return KXPU_E_INVALID;
+    *n_rows = t->n_rows;
+    return KXPU_OK;
+}
+
+extern "C" int32_t kxpu_table_export(kxpu_ctx *ctx, kxpu_table *t, uint32_t *keys, uint64_t *line_off, int32_t *rows,
+                                     size_t cap, uint32_t *n_rows) {
+    KX_ENTER(ctx);
+    if (!t || !n_rows) return KXPU_E_INVALID;
+    *n_rows = t->n_rows;
+    if (cap < t->n_rows) return KXPU_E_NOSPACE;
+    if (t->n_rows == 0) return KXPU_OK;
+    if (!keys || !line_off || !rows) return KXPU_E_INVALID;
+    std::vector<uint32_t> k(t->n_rows);
+    std::vector<unsigned long long> l(t->n_rows);
+    KX_CUDA(ctx, cudaMemcpyAsync(k.data(), t->row_key, t->n_rows * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+    KX_CUDA(ctx, cudaMemcpyAsync(l.data(), t->row_line, t->n_rows * 8ull, cudaMemcpyDeviceToHost, ctx->stream));
+    KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> order(t->n_rows);
+    for (uint32_t i = 0; i < t->n_rows; i++) order[i] = (int32_t)i;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return l[a] < l[b]; });  // file order
+    for (uint32_t i = 0; i < t->n_rows; i++) {
+        keys[i] = k[order[i]];
+        line_off[i] = l[order[i]];
+        rows[i] = order[i];
+    }
+    return KXPU_OK;
+}
+
+// ------------------------------------------------------------------ lookup / names
+static int32_t launch_lookup(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *d_keys, size_t n, int32_t *d_rows) {
+    if (n == 0) return KXPU_OK;
+    KxTimer tm(ctx, KXPU_T_LOOKUP);
+    size_t blocks = (n + 255) / 256;
+    size_t maxb = (size_t)ctx->sm_count * 32;
+    if (blocks > maxb) blocks = maxb;
+    kxparse::lookup_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_keys, n, t->dev.keys, t->row_of_slot, t->cap,
+                                                                     t->shift, d_rows);
+    KX_LAUNCHED(ctx);
+    KX_CUDA(ctx, cudaGetLastError());
+    return KXPU_OK;
+}
+
+extern "C" int32_t kxpu_lookup_device(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *d_keys, size_t n,
+                                      int32_t *d_rows_out) {
+    KX_ENTER(ctx);
+    if (!t || (n && (!d_keys || !d_rows_out))) return KXPU_E_INVALID;
+    kx_clear_timings(ctx);
+    return launch_lookup(ctx, t, d_keys, n, d_rows_out);
+}
+
+extern "C" int32_t kxpu_lookup(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *keys, size_t n, int32_t *rows_out) {
+    KX_ENTER(ctx);
+    if (!t || (n && (!keys || !rows_out))) return KXPU_E_INVALID;
+    kx_clear_timings(ctx);
+    if (n == 0) return KXPU_OK;
+    uint32_t *d_keys = nullptr;
+    int32_t *d_rows = nullptr;
+    KX_CUDA(ctx, cudaMallocAsync((void **)&d_keys, n * 4, ctx->stream));
+    KX_CUDA(ctx, cudaMallocAsync((void **)&d_rows, n * 4, ctx->stream));
+    cudaMemcpyAsync(d_keys, keys, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    int32_t rc = launch_lookup(ctx, t, d_keys, n, d_rows);
+    cudaMemcpyAsync(rows_out, d_rows, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaFreeAsync(d_keys, ctx->stream);
+    cudaFreeAsync(d_rows, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc == KXPU_OK && e != cudaSuccess) { KX_SET_ERR(ctx, "lookup failed: %s", cudaGetErrorString(e)); rc = KXPU_E_CUDA; }
+    return rc;
+}
+
+extern "C" int32_t kxpu_names(kxpu_ctx *ctx, kxpu_table *t, const int32_t *rows, size_t n, uint8_t *out, size_t cap,
+                              uint32_t *offsets, size_t *need) {
+    KX_ENTER(ctx);
+    if (!t || !offsets || (n && !rows)) return KXPU_E_INVALID;
+    kx_clear_timings(ctx);
+    if (n == 0) { offsets[0] = 0; if (need) *need = 0; return KXPU_OK; }
+    int32_t *d_rows = nullptr;
+    uint32_t *d_lens = nullptr, *d_offs = nullptr;
+    unsigned long long *d_part = nullptr;
+    uint8_t *d_out = nullptr;
+    const size_t np = kxscan::scratch_items(n + 1);
+    KX_CUDA(ctx, cudaMallocAsync((void **)&d_rows, n * 4, ctx->stream));
+    KX_CUDA(ctx, cudaMallocAsync((void **)&d_lens, (n + 1) * 4, ctx->stream));
+    KX_CUDA(ctx, cudaMallocAsync((void **)&d_offs, (n + 1) * 4, ctx->stream));
+    KX_CUDA(ctx, cudaMallocAsync((void **)&d_part, (np + 1) * 8, ctx->stream));
+    cudaMemcpyAsync(d_rows, rows, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(d_lens + n, 0, 4, ctx->stream);
+    int32_t rc = KXPU_OK;
+    {
+        KxTimer tm(ctx, KXPU_T_NAMES);
+        kxparse::name_len_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_rows, n, t->row_name_len,
+                                                                                       t->n_rows, d_lens);
+        KX_LAUNCHED(ctx);
+        // scanning n+1 items makes offsets[n] the total
+        kxscan::exclusive_scan<uint32_t>(ctx, d_lens, n + 1, d_offs, d_part, d_part + np);
+    }
+    cudaMemcpyAsync(offsets, d_offs, (n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { KX_SET_ERR(ctx, "names failed: %s", cudaGetErrorString(e)); rc = KXPU_E_CUDA; }
+    size_t total = rc == KXPU_OK ? offsets[n] : 0;
+    if (need) *need = total;
+    if (rc == KXPU_OK && total > cap) rc = KXPU_E_NOSPACE;
+    if (rc == KXPU_OK && total > 0) {
+        if (!out) rc = KXPU_E_INVALID;
+        else {
+            e = cudaMallocAsync((void **)&d_out, total, ctx->stream);
+            if (e == cudaSuccess) {
+                kxparse::name_copy_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, ctx->stream>>>(
+                    d_rows, n, t->row_name_off, t->row_name_len, t->n_rows, t->blob, d_offs, d_out, total);
+                KX_LAUNCHED(ctx);
+                cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream);
+                cudaFreeAsync(d_out, ctx->stream);
+                e = cudaStreamSynchronize(ctx->stream);
+            }
+            if (e != cudaSuccess) { KX_SET_ERR(ctx, "names copy failed: %s", cudaGetErrorString(e)); rc = KXPU_E_CUDA; }
+        }
+    }
+    cudaFreeAsync(d_rows, ctx->stream);
+    cudaFreeAsync(d_lens, ctx->stream);
+    cudaFreeAsync(d_offs, ctx->stream);
+    cudaFreeAsync(d_part, ctx->stream);
+    return rc;
+}
