@@ -12,6 +12,8 @@
 //   iommuMap CSR  = accepted records stably sorted by group ordinal -> LSD radix sort
 //   deviceMap     = groups keyed by the device id of their first member, ids ordered by
 //                   first appearance; CSR by a second stable sort.
+#include <utility>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -96,8 +98,7 @@ __global__ void __launch_bounds__(256) k_candidates(const Work W) {
     if (i >= W.n) return;
     // one 64-byte record per thread: four 16-byte vector loads
     const uint4 *rp = reinterpret_cast<const uint4 *>(W.recs + i);
-    uint4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3];
-    (void)q0;
+    uint4 q1 = rp[1], q2 = rp[2], q3 = rp[3];  // rp[0] is the bdf: not needed to classify
     const uint8_t *vtxt = reinterpret_cast<const uint8_t *>(&q1);      // vendor_txt[8], device_txt[8]
     const uint8_t *dtxt = vtxt + 8;
     const unsigned long long drv0 = ((unsigned long long)q2.y << 32) | q2.x;  // driver[0..8)
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256) k_candidates(const Work W) {
                 vid == 0x65643031ull /* "10de" */ && !(fl & KXPU_REC_DRIVER_ERR) &&
                 drv0 == 0x6963702d6f696676ull /* "vfio-pci" */ && drv8 == 0u && !(fl & KXPU_REC_IOMMU_ERR);
     bool dok = !(fl & KXPU_REC_DEVICE_ERR) && read_id(dtxt, dlen, did, dl);
+    if (!(fl & (KXPU_REC_IS_DIR | KXPU_REC_VENDOR_ERR)) && vlen > 8u) W.flags[0] = 1u;
     if (cand && (group == EMPTY32 || (dok && did == EMPTY64) || (!(fl & KXPU_REC_DEVICE_ERR) && dlen > 8u)))
         W.flags[0] = 1u;  // outside the supported domain
     uint32_t slot = EMPTY32;

@@ -39,7 +39,7 @@ __device__ __forceinline__ uint32_t block_excl(uint32_t v, uint32_t *tot) {
     return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) reduce_kernel(const uint32_t *__restrict__ in, size_t n,
+static __global__ void __launch_bounds__(SCAN_THREADS) reduce_kernel(const uint32_t *__restrict__ in, size_t n,
                                                               unsigned long long *__restrict__ partial) {
     size_t base = (size_t)blockIdx.x * SCAN_TILE;
     uint32_t s = 0;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) reduce_kernel(const uint32_t *__
 }
 
 // single block: exclusive scan of the per-block partials (64-bit), writes grand total.
-__global__ void __launch_bounds__(1024) partial_scan_kernel(unsigned long long *partial, size_t nb,
+static __global__ void __launch_bounds__(1024) partial_scan_kernel(unsigned long long *partial, size_t nb,
                                                              unsigned long long *total_out) {
     __shared__ unsigned long long carry;
     __shared__ unsigned long long wsum[32];

@@ -107,9 +107,9 @@ def scan_lookup(text, vendor: bytes, device: bytes):
 def device_name(text, key: int):
     """(line_off, name bytes) with name=None on a miss."""
     p, n, keep = _buf(text)
-    out = C.create_string_buffer(1024)
+    out = C.create_string_buffer(65536)
     off = C.c_int64(0)
-    l = lib().kxo_device_name(p, n, key, out, 1024, C.byref(off), None)
+    l = lib().kxo_device_name(p, n, key, out, 65536, C.byref(off), None)
     return (off.value, None) if l < 0 else (off.value, out.raw[:l])
 
 

@@ -1,0 +1,206 @@
+"""GPU parity tests of the pci.ids path (K1-K4) through the C ABI, against the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import pyref
+from test_oracle import EDGE_TEXTS
+
+pytestmark = pytest.mark.gpu
+
+
+def table_as_dict(kx, tab):
+    keys, offs, rows = kx.table_export(tab)
+    names, _, _ = kx.names(tab, rows)
+    return keys, offs, rows, names
+
+
+def check_text(kx, oracle, text, extra_keys=()):
+    """Full-table and per-key parity of one text against the oracle."""
+    tab = kx.pciids_load(text)
+    try:
+        keys, offs, rows, names = table_as_dict(kx, tab)
+        orows = oracle.table_build(text)
+        assert np.array_equal(keys, orows["key"])
+        assert np.array_equal(offs, orows["line_off"])
+        for k, o, nm in zip(keys[:200], offs[:200], names[:200]):
+            assert nm == oracle.row_name(text, int(o))
+        q = np.array(list(keys[:64]) + list(extra_keys), dtype=np.uint32)
+        if len(q):
+            r = kx.lookup(tab, q)
+            gn, _, _ = kx.names(tab, r)
+            line_of_row = dict(zip(rows.tolist(), offs.tolist()))
+            for k, row, nm in zip(q, r, gn):
+                ooff, oname = oracle.device_name(text, int(k))
+                assert (line_of_row[int(row)] if row >= 0 else -1) == ooff, hex(int(k))
+                assert nm == (oname or b"")
+    finally:
+        tab.free()
+
+
+def test_cfg2_full_pci_ids(kx, oracle, pci_text, oracle_rows, golden, workloads):
+    """BASELINE.json configs[1]: full utils/pci.ids parse + 1024 synthetic lookups, bit-exact."""
+    tab = kx.pciids_load(pci_text)
+    keys, offs, rows, names = table_as_dict(kx, tab)
+    assert tab.rows == golden["rows"]
+    assert np.array_equal(keys, oracle_rows["key"]) and np.array_equal(offs, oracle_rows["line_off"])
+    dump = b"".join(b"%04x:%04x\t%s\n" % (k >> 16, k & 0xFFFF, nm) for k, nm in zip(keys, names))
+    assert hashlib.sha256(dump).hexdigest() == golden["dump_sha256"]
+    q = workloads.cfg2_queries(oracle_rows["key"])
+    r = kx.lookup(tab, q)
+    assert int((r >= 0).sum()) == 768
+    ooffs, onames = oracle.lookup_many(pci_text, q)
+    line_of_row = dict(zip(rows.tolist(), offs.tolist()))
+    got = np.array([line_of_row[x] if x >= 0 else -1 for x in r.tolist()], dtype=np.int64)
+    assert np.array_equal(got, ooffs)
+    gn, _, _ = kx.names(tab, r)
+    assert gn == [n or b"" for n in onames]
+    for k, want in golden["spots"].items():
+        row = kx.lookup(tab, np.array([int(k, 16)], np.uint32))
+        nm = kx.names(tab, row)[0][0]
+        assert nm.decode() == (want["name"] or "")
+    tab.free()
+
+
+@pytest.mark.parametrize("text", EDGE_TEXTS)
+def test_edge_texts(kx, oracle, text):
+    check_text(kx, oracle, text, extra_keys=[0x10de2330, 0x10de0001, 0x10de0002, 0x10df0001, 0, 0xffffffff])
+
+
+def test_ragged_sizes_around_tile_boundaries(kx, oracle, pci_text):
+    """Tile = 16 KiB, TMA stage has 16-byte halos: cut the text at awkward lengths."""
+    for n in [1, 5, 15, 16, 17, 16383, 16384, 16385, 16399, 16400, 16401, 32767, 32768, 32769, 49152 + 7, 100001]:
+        check_text(kx, oracle, pci_text[:n])
+
+
+def test_key_ffffffff_and_illegal_vendor(kx, oracle):
+    text = b"ffff  Illegal Vendor ID\n\tffff  all ones\n\t0000  zeros\n0000  zero vendor\n\t0000  z\n"
+    check_text(kx, oracle, text, extra_keys=[0xffffffff, 0xffff0000, 0, 0x0000ffff])
+
+
+def test_duplicate_vendor_blocks_first_wins(kx, oracle, pci_text):
+    """x3 replication: every key has three occurrences, the first wins; a vendor whose device
+    only appears under a LATER anchor must miss."""
+    text = pci_text[:200000]
+    text = text[:text.rfind(b"\n") + 1]
+    check_text(kx, oracle, text * 3)
+    tricky = b"10de  first\n\t0001  a\n10df  x\n10de  again\n\t0002  hidden\n" * 50
+    check_text(kx, oracle, tricky, extra_keys=[0x10de0002, 0x10de0001])
+
+
+def test_long_block_needs_tile_lookback(kx, oracle):
+    """A vendor block spanning many 16 KiB tiles: device lines far from their vendor line
+    resolve through the decoupled look-back carry."""
+    lines = [b"abcd  Big vendor\n"]
+    for d in range(20000):
+        lines.append(b"\t%04x  Device number %d\n" % (d, d))
+        if d % 7 == 0:
+            lines.append(b"\t\t1234 %04x  subsystem\n" % d)
+        if d % 13 == 0:
+            lines.append(b"# comment\n")
+    lines.append(b"abce  Next\n\t0001  n\n")
+    text = b"".join(lines)
+    assert len(text) > 30 * 16384
+    check_text(kx, oracle, text, extra_keys=[0xabcd0000, 0xabcd4e1f, 0xabce0001, 0xabcd4e20])
+
+
+def test_too_long_line(kx, oracle):
+    ok_line = b"#" + b"x" * 65534
+    bad_line = b"#" + b"x" * 65535
+    for mid in (ok_line, bad_line):
+        text = b"10de  NV\n\t0001  a\n" + mid + b"\n\t0002  b\n10df  v\n\t0003  c\n"
+        check_text(kx, oracle, text, extra_keys=[0x10de0001, 0x10de0002, 0x10df0003])
+    # unterminated, too long final line
+    text = b"10de  NV\n\t0001  a\n10df  v\n\t0003  " + b"y" * 70000
+    check_text(kx, oracle, text, extra_keys=[0x10de0001, 0x10df0003])
+    # long but legal device name (slow path of the sanitiser)
+    text = b"10de  NV\n\t0001  " + b"Ab.c " * 2000 + b"\n\t0002  z\n"
+    check_text(kx, oracle, text, extra_keys=[0x10de0001, 0x10de0002])
+
+
+def test_unicode_and_crlf_names(kx, oracle):
+    text = (b"10de  NV\r\n\t0001  Wi-Fi\xc2\xae 5 \xc2\xa0\r\n\t0002  d\xc4\xb1g \xc5\xbf\n\t0003   \n\t0004\n"
+            b"\t0005  a\tb \x0b c \n\t0006  \xe2\x80\x83em\xe3\x80\x80\n\t0007  \xff\xfe ok\n")
+    check_text(kx, oracle, text, extra_keys=[0x10de0000 + i for i in range(1, 9)])
+
+
+def test_random_pciids_shaped_texts(kx, oracle):
+    """Seeded random texts with the pci.ids grammar plus noise (blank lines, class section,
+    duplicate vendors, upper-case hex, short lines)."""
+    rng = np.random.default_rng(2024)
+    for trial in range(12):
+        lines = []
+        for _ in range(int(rng.integers(5, 400))):
+            r = rng.random()
+            v = int(rng.integers(0, 40)) * 0x0101
+            if r < 0.2:
+                lines.append(b"%04x  Vendor %d\n" % (v, v))
+            elif r < 0.7:
+                lines.append(b"\t%04x  Dev.%d / x\n" % (int(rng.integers(0, 60)), int(rng.integers(0, 1000))))
+            elif r < 0.8:
+                lines.append(b"\t\t%04x %04x  Sub\n" % (v, v))
+            elif r < 0.85:
+                lines.append(b"# c\n")
+            elif r < 0.88:
+                lines.append(b"\n")
+            elif r < 0.91:
+                lines.append(b"C %02x  Class\n" % int(rng.integers(0, 255)))
+            elif r < 0.94:
+                lines.append(b"\t%04X  UPPER\n" % int(rng.integers(0xa000, 0xffff)))
+            elif r < 0.97:
+                lines.append(b"\t12\n")
+            else:
+                lines.append(b"%04x\n" % v)
+        text = b"".join(lines)
+        if trial % 3 == 0:
+            text = text.rstrip(b"\n")
+        keys = [(int(rng.integers(0, 40)) * 0x0101 << 16) | int(rng.integers(0, 60)) for _ in range(40)]
+        check_text(kx, oracle, text, extra_keys=keys)
+
+
+def test_x1000_first_occurrence_wins(kx, oracle, pci_text, oracle_rows, workloads):
+    """BASELINE.json configs[3] at full size on one GPU: 1.458 GB text, 2^20 keys; the table
+    must equal the single-copy table (size-independent property) and every lookup must agree
+    with it."""
+    n, copies = len(pci_text), 1000
+    d_one = kx.dev_alloc(n)
+    kx.upload(d_one, np.frombuffer(pci_text, np.uint8))
+    d_big = kx.dev_alloc(n * copies)
+    kx.replicate(d_big, d_one, n, copies)
+    tab = kx.pciids_load_device(d_big, n * copies)
+    keys, offs, rows = kx.table_export(tab)
+    assert np.array_equal(keys, oracle_rows["key"]) and np.array_equal(offs, oracle_rows["line_off"])
+    q = workloads.cfg4_queries(oracle_rows["key"])
+    r = kx.lookup(tab, q)
+    # oracle via the single-copy table (identical by the property above)
+    order = np.argsort(oracle_rows["key"])
+    sk = oracle_rows["key"][order]
+    pos = np.searchsorted(sk, q)
+    pos[pos >= len(sk)] = 0
+    hit = sk[pos] == q
+    want = np.where(hit, oracle_rows["line_off"][order][pos].astype(np.int64), -1)
+    line_of_row = np.full(tab.rows + 1, -1, np.int64)
+    line_of_row[rows] = offs.astype(np.int64)
+    got = np.where(r >= 0, line_of_row[np.maximum(r, 0)], -1)
+    assert np.array_equal(got, want)
+    assert int(hit.sum()) == int((r >= 0).sum()) == 786432
+    tab.free()
+    kx.dev_free(d_big)
+    kx.dev_free(d_one)
+
+
+def test_names_nospace_and_empty(kx, pci_text):
+    import ctypes as C
+    tab = kx.pciids_load(pci_text)
+    rows = kx.lookup(tab, np.array([0x10de2330, 0x10de2901], np.uint32))
+    assert rows[0] >= 0 and rows[1] == -1
+    names, blob, offs = kx.names(tab, rows)
+    assert names == [b"GH100_H100_SXM5_80GB", b""]
+    offs2 = np.empty(3, np.uint32)
+    need = C.c_size_t(0)
+    out = np.empty(4, np.uint8)
+    rc = kx.L.kxpu_names(kx.ctx, tab.handle, rows.ctypes.data, 2, out.ctypes.data, 4, offs2.ctypes.data, C.byref(need))
+    assert rc == -4 and need.value == 20
+    assert kx.lookup(tab, np.empty(0, np.uint32)).size == 0
+    tab.free()
