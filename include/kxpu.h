@@ -71,6 +71,11 @@ uint64_t kxpu_launch_count(kxpu_ctx *ctx);
 #define KXPU_T_MERGE    6
 #define KXPU_T_COUNT    8
 int32_t kxpu_last_timings(kxpu_ctx *ctx, float ms_out[KXPU_T_COUNT]);
+/* Device-side stopwatch over an arbitrary sequence of calls on this ctx: begin records a
+ * CUDA event on the ctx stream, end records a second one, waits for it and returns the
+ * elapsed milliseconds (bench.py times its K steps with this pair). */
+int32_t kxpu_timer_begin(kxpu_ctx *ctx);
+int32_t kxpu_timer_end(kxpu_ctx *ctx, float *ms_out);
 
 /* Device / pinned memory helpers so a host program without a CUDA binding can keep
  * inputs resident (used by bench.py for the HBM-resident `value` measurement and for

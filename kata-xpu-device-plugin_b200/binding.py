@@ -30,7 +30,7 @@ assert DEVREC_DTYPE.itemsize == 64 and CDIDEV_DTYPE.itemsize == 32
 # every symbol include/kxpu.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "kxpu_ctx_create", "kxpu_ctx_destroy", "kxpu_strerror", "kxpu_last_error", "kxpu_launch_count",
-    "kxpu_last_timings", "kxpu_dev_alloc", "kxpu_dev_free", "kxpu_dev_upload", "kxpu_dev_download",
+    "kxpu_last_timings", "kxpu_timer_begin", "kxpu_timer_end", "kxpu_dev_alloc", "kxpu_dev_free", "kxpu_dev_upload", "kxpu_dev_download",
     "kxpu_dev_replicate", "kxpu_pinned_alloc", "kxpu_pinned_free", "kxpu_sync", "kxpu_pciids_load",
     "kxpu_pciids_load_device", "kxpu_table_free", "kxpu_table_rows", "kxpu_table_export", "kxpu_lookup",
     "kxpu_lookup_device", "kxpu_names", "kxpu_comm_unique_id", "kxpu_comm_init", "kxpu_comm_destroy",
@@ -75,6 +75,8 @@ def load_library():
         "kxpu_last_error": (C.c_char_p, [vp]),
         "kxpu_launch_count": (u64, [vp]),
         "kxpu_last_timings": (i32, [vp, C.POINTER(C.c_float)]),
+        "kxpu_timer_begin": (i32, [vp]),
+        "kxpu_timer_end": (i32, [vp, C.POINTER(C.c_float)]),
         "kxpu_dev_alloc": (i32, [vp, sz, C.POINTER(vp)]),
         "kxpu_dev_free": (i32, [vp, vp]),
         "kxpu_dev_upload": (i32, [vp, vp, vp, sz]),
@@ -158,6 +160,14 @@ class Kxpu:
 
     def sync(self):
         self._chk(self.L.kxpu_sync(self.ctx))
+
+    def timer_begin(self):
+        self._chk(self.L.kxpu_timer_begin(self.ctx))
+
+    def timer_end(self):
+        ms = C.c_float(0)
+        self._chk(self.L.kxpu_timer_end(self.ctx, C.byref(ms)))
+        return ms.value
 
     # -- memory
     def dev_alloc(self, nbytes):

@@ -4,6 +4,9 @@
 #include <vector>
 
 #include "pciids.cu"  // kernels (single translation unit keeps them inlinable and static)
+#include "pciids2.cu"
+
+#include <cstdlib>
 
 struct kxpu_table {
     uint32_t cap = 0, shift = 0;
@@ -57,6 +60,8 @@ extern "C" int32_t kxpu_ctx_create(int32_t ordinal, kxpu_ctx **out) {
         return KXPU_E_CUDA;
     }
     for (int i = 0; i < 2 * KXPU_T_COUNT; i++) cudaEventCreate(&c->ev[i]);
+    cudaEventCreate(&c->ev_user[0]);
+    cudaEventCreate(&c->ev_user[1]);
     cudaMallocHost((void **)&c->h_ctl, 64 * sizeof(uint32_t));
     // keep stream-ordered allocations cached: table builds allocate/free per call
     cudaMemPool_t pool;
@@ -66,6 +71,10 @@ extern "C" int32_t kxpu_ctx_create(int32_t ordinal, kxpu_ctx **out) {
     }
     cudaFuncSetAttribute(kxparse::parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(kxparse::ParseSmem));
+    cudaFuncSetAttribute(kxparse2::parse_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(kxparse2::WarpSmem) * kxparse2::WARPS));
+    const char *pv = getenv("KXPU_PARSE_V");  // 1 = CTA-tiled kernel (pciids.cu), 2 = warp-autonomous (default)
+    c->parse_version = (pv && pv[0] == '1') ? 1 : 2;
     *out = c;
     return KXPU_OK;
 }
@@ -75,6 +84,8 @@ extern "C" int32_t kxpu_ctx_destroy(kxpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2 * KXPU_T_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaEventDestroy(ctx->ev_user[0]);
+    cudaEventDestroy(ctx->ev_user[1]);
     cudaFreeHost(ctx->h_ctl);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -98,6 +109,20 @@ extern "C" int32_t kxpu_last_timings(kxpu_ctx *ctx, float ms_out[KXPU_T_COUNT]) 
     if (!(ctx)) return KXPU_E_INVALID;         \
     std::lock_guard<std::mutex> guard__((ctx)->mu); \
     cudaSetDevice((ctx)->device)
+
+extern "C" int32_t kxpu_timer_begin(kxpu_ctx *ctx) {
+    KX_ENTER(ctx);
+    KX_CUDA(ctx, cudaEventRecord(ctx->ev_user[0], ctx->stream));
+    return KXPU_OK;
+}
+extern "C" int32_t kxpu_timer_end(kxpu_ctx *ctx, float *ms_out) {
+    KX_ENTER(ctx);
+    if (!ms_out) return KXPU_E_INVALID;
+    KX_CUDA(ctx, cudaEventRecord(ctx->ev_user[1], ctx->stream));
+    KX_CUDA(ctx, cudaEventSynchronize(ctx->ev_user[1]));
+    KX_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev_user[0], ctx->ev_user[1]));
+    return KXPU_OK;
+}
 
 extern "C" int32_t kxpu_dev_alloc(kxpu_ctx *ctx, size_t bytes, void **d_out) {
     KX_ENTER(ctx);
@@ -233,6 +258,17 @@ static int parse_grid(kxpu_ctx *ctx, uint32_t num_tiles) {
     return (int)(g < 1 ? 1 : g);
 }
 
+static int parse_grid_v2(kxpu_ctx *ctx, uint32_t num_chunks) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kxparse2::parse_kernel_v2, kxparse2::NT,
+                                                  sizeof(kxparse2::WarpSmem) * kxparse2::WARPS);
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)per_sm * ctx->sm_count;
+    long long need = ((long long)num_chunks + kxparse2::WARPS - 1) / kxparse2::WARPS;
+    if (g > need) g = need;
+    return (int)(g < 1 ? 1 : g);
+}
+
 static int32_t launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n,
                                unsigned long long base, int check_valid) {
     kxparse::FinalizeParams F;
@@ -256,7 +292,9 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
         return KXPU_E_INVALID;
     }
     if (base + n >= (1ull << 44)) return KXPU_E_UNSUPPORTED;
-    const uint32_t num_tiles = (uint32_t)((n + kxparse::T - 1) / kxparse::T);
+    const bool v2 = ctx->parse_version == 2;
+    const uint32_t tile_bytes = v2 ? (uint32_t)kxparse2::CW : (uint32_t)kxparse::T;
+    const uint32_t num_tiles = (uint32_t)((n + tile_bytes - 1) / tile_bytes);
     uint32_t cap = 1u << 16;
     uint32_t blob_cap = (uint32_t)std::min<size_t>(std::max<size_t>(n, 256), 4u << 20);
     for (int attempt = 0; attempt < 8; attempt++) {
@@ -265,10 +303,18 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
         if (rc != KXPU_OK) return rc;
         if (num_tiles > 0) {
             KxTimer tm(ctx, KXPU_T_PARSE);
-            kxparse::ParseParams P;
-            P.text = d_text; P.n = n; P.base = base; P.num_tiles = num_tiles;
-            P.tile_state = t->tile_state; P.tab = t->dev; P.carry_in = carry_in;
-            kxparse::parse_kernel<<<parse_grid(ctx, num_tiles), kxparse::NT, sizeof(kxparse::ParseSmem), ctx->stream>>>(P);
+            if (v2) {
+                kxparse2::Params P;
+                P.text = d_text; P.n = n; P.base = base; P.num_chunks = num_tiles;
+                P.chunk_state = t->tile_state; P.tab = t->dev; P.carry_in = carry_in;
+                const size_t smem = sizeof(kxparse2::WarpSmem) * kxparse2::WARPS;
+                kxparse2::parse_kernel_v2<<<parse_grid_v2(ctx, num_tiles), kxparse2::NT, smem, ctx->stream>>>(P);
+            } else {
+                kxparse::ParseParams P;
+                P.text = d_text; P.n = n; P.base = base; P.num_tiles = num_tiles;
+                P.tile_state = t->tile_state; P.tab = t->dev; P.carry_in = carry_in;
+                kxparse::parse_kernel<<<parse_grid(ctx, num_tiles), kxparse::NT, sizeof(kxparse::ParseSmem), ctx->stream>>>(P);
+            }
             KX_LAUNCHED(ctx);
         }
         {
@@ -283,6 +329,10 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
             table_release(ctx, t);
             return KXPU_E_CUDA;
         }
+#ifdef KX_DEBUG_COUNTERS
+        fprintf(stderr, "[kxpu dbg] lookbacks %u poll %u sleep_unready_near %u hops %u sleep_noprefix %u\n", ctx->h_ctl[8],
+                ctx->h_ctl[9], ctx->h_ctl[10], ctx->h_ctl[11], ctx->h_ctl[12]);
+#endif
         if (ctx->h_ctl[KX_C_NEED_TRUNC] == 2u) {
             // a >= 1 KiB stretch without a line start was seen: compute the exact
             // bufio.ErrTooLong cut-off and finalize again.

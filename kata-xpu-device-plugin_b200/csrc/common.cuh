@@ -14,6 +14,7 @@ struct kxpu_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2 * KXPU_T_COUNT] = {};
+    cudaEvent_t ev_user[2] = {};
     bool ev_used[KXPU_T_COUNT] = {};
     uint64_t launches = 0;
     std::mutex mu;
@@ -23,6 +24,7 @@ struct kxpu_ctx {
     // NCCL (lazy)
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    int parse_version = 2;
 };
 
 #define KX_SET_ERR(ctx, ...) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__)

@@ -1,0 +1,466 @@
+// device_plugin.cpp -- see device_plugin.hpp.  Reference: pkg/device_plugin/device_plugin.go,
+// pkg/device_plugin/generic_device_plugin.go, cdi/spec.go (citations per function).
+#include "device_plugin.hpp"
+
+#include <dirent.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+
+namespace device_plugin {
+
+static const char *kDevicePluginPath = "/var/lib/kubelet/device-plugins/";  // pluginapi.DevicePluginPath
+static const char *kHealthy = "Healthy";                                     // pluginapi.Healthy
+static const char *kK8SCDIVendorClass = "KUBERNETES_CDI_VENDOR_CLASS";       // generic_device_plugin.go:29
+static const char *kCdiVendorClass = "nvidia.com/gpu";                       // generic_device_plugin.go:30
+
+static Error fail(const std::string &m) { Error e; e.failed = true; e.message = m; return e; }
+static Error kxfail(kxpu_ctx *ctx, const char *what, int32_t rc) {
+    return fail(std::string(what) + ": " + kxpu_strerror(rc) + " (" + kxpu_last_error(ctx) + ")");
+}
+
+// readIDFromFileFunc, device_plugin.go:183-191 -- the os.ReadFile half.  Returns the RAW file
+// bytes: the data[2:] / Trim("\n") half of :189 runs on the GPU (kxpu_classify).
+static bool readIDFromFileFunc(const std::string &base, const std::string &addr, const std::string &prop, std::string &out) {
+    std::string path = base + "/" + addr + "/" + prop;  // filepath.Join
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) {
+        fprintf(stderr, "Could not read %s for device %s: %s\n", prop.c_str(), addr.c_str(), strerror(errno));
+        return false;
+    }
+    char buf[256];
+    size_t n = fread(buf, 1, sizeof buf, f);
+    bool err = ferror(f) != 0;
+    fclose(f);
+    if (err) return false;
+    out.assign(buf, n);
+    return true;
+}
+
+// readLinkFunc, device_plugin.go:194-202: os.Readlink + last path element.
+static bool readLinkFunc(const std::string &base, const std::string &addr, const std::string &link, std::string &out) {
+    std::string path = base + "/" + addr + "/" + link;
+    char buf[4096];
+    ssize_t n = readlink(path.c_str(), buf, sizeof buf - 1);
+    if (n < 0) {
+        fprintf(stderr, "Could not read link %s for device %s: %s\n", link.c_str(), addr.c_str(), strerror(errno));
+        return false;
+    }
+    std::string target(buf, (size_t)n);
+    size_t slash = target.find_last_of('/');  // filepath.Split
+    out = slash == std::string::npos ? target : target.substr(slash + 1);
+    return true;
+}
+
+Plugin::Plugin(kxpu_ctx *ctx) : ctx_(ctx) {
+    readLink = readLinkFunc;
+    readIDFromFile = readIDFromFileFunc;
+    returnIommuMap = [this]() -> const OrderedMap<std::vector<NvidiaGpuDevice>> & { return iommuMap; };
+}
+
+Plugin::~Plugin() {
+    if (table_) kxpu_table_free(ctx_, table_);
+}
+
+// filepath.Walk(basePath, ...) (device_plugin.go:132): lexical order, os.Lstat (symlinks are not
+// followed, so a real sysfs entry is "not a directory"), directories are descended into and
+// reported as "Not a device" (:137-140).
+static Error walkDir(Plugin &p, const std::string &path, const std::string &name, std::vector<kxpu_devrec> &recs) {
+    struct stat sb;
+    if (lstat(path.c_str(), &sb) != 0) return fail("Error accessing file path \"" + path + "\": " + strerror(errno));  // :133-136
+    if (S_ISDIR(sb.st_mode)) {
+        DIR *d = opendir(path.c_str());
+        if (!d) return fail("Error accessing file path \"" + path + "\": " + strerror(errno));
+        std::vector<std::string> names;
+        while (struct dirent *de = readdir(d)) {
+            if (strcmp(de->d_name, ".") == 0 || strcmp(de->d_name, "..") == 0) continue;
+            names.push_back(de->d_name);
+        }
+        closedir(d);
+        std::sort(names.begin(), names.end());
+        for (const std::string &n : names) {
+            Error e = walkDir(p, path + "/" + n, n, recs);
+            if (e) return e;
+        }
+        return Error();
+    }
+    // one raw record per non-directory entry; every read goes through the seams and is keyed by
+    // info.Name() under basePath exactly like :142,:151,:157,:164
+    kxpu_devrec r;
+    memset(&r, 0, sizeof r);
+    std::string s;
+    bool vendor_ok = p.readIDFromFile(p.basePath, name, "vendor", s);
+    if (!vendor_ok) {
+        r.flags |= KXPU_REC_VENDOR_ERR;  // "Could not get vendor ID for device" -> skipped
+        strncpy(r.bdf, name.c_str(), sizeof r.bdf - 1);
+        recs.push_back(r);
+        return Error();
+    }
+    if (name.size() > sizeof r.bdf - 1) return fail("PCI address longer than 15 bytes: " + name);
+    memcpy(r.bdf, name.data(), name.size());
+    r.vendor_len = (uint8_t)std::min<size_t>(s.size(), 255);
+    memcpy(r.vendor_txt, s.data(), std::min<size_t>(s.size(), 8));
+    if (p.readLink(p.basePath, name, "driver", s)) {
+        memcpy(r.driver, s.data(), std::min<size_t>(s.size(), sizeof r.driver - 1));
+    } else {
+        r.flags |= KXPU_REC_DRIVER_ERR;
+    }
+    if (p.readLink(p.basePath, name, "iommu_group", s)) {
+        bool dec = !s.empty() && s.size() <= 10;
+        unsigned long long v = 0;
+        for (char c : s) { if (c < '0' || c > '9') dec = false; else v = v * 10 + (unsigned)(c - '0'); }
+        if (!dec || v >= 0xFFFFFFFFull || (s.size() > 1 && s[0] == '0'))
+            return fail("iommu_group of " + name + " is not a canonical decimal number: " + s);
+        r.iommu_group = (uint32_t)v;
+    } else {
+        r.flags |= KXPU_REC_IOMMU_ERR;
+    }
+    if (p.readIDFromFile(p.basePath, name, "device", s)) {
+        r.device_len = (uint8_t)std::min<size_t>(s.size(), 255);
+        memcpy(r.device_txt, s.data(), std::min<size_t>(s.size(), 8));
+    } else {
+        r.flags |= KXPU_REC_DEVICE_ERR;
+    }
+    recs.push_back(r);
+    return Error();
+}
+
+Error Plugin::gatherRecords(std::vector<kxpu_devrec> &recs) {
+    recs.clear();
+    size_t slash = basePath.find_last_of('/');
+    return walkDir(*this, basePath, slash == std::string::npos ? basePath : basePath.substr(slash + 1), recs);
+}
+
+static std::string devIdString(uint64_t packed) {
+    char b[9];
+    memcpy(b, &packed, 8);
+    b[8] = 0;
+    return std::string(b);
+}
+
+// createIommuDeviceMap, device_plugin.go:126-180
+Error Plugin::createIommuDeviceMap() {
+    iommuMap.clear();   // :127
+    deviceMap.clear();  // :128
+    std::vector<kxpu_devrec> recs;
+    Error e = gatherRecords(recs);
+    if (e) { fprintf(stderr, "%s\n", e.message.c_str()); }  // Walk's error is ignored by the reference (:132)
+    const size_t n = recs.size();
+    std::vector<uint32_t> accept(n), gids(n), goff(n + 1), gmem(n), doff(n + 1), dgrp(n);
+    std::vector<uint64_t> dids(n);
+    kxpu_classify_out out;
+    memset(&out, 0, sizeof out);
+    out.accept_index = accept.data(); out.group_ids = gids.data(); out.group_off = goff.data();
+    out.group_members = gmem.data(); out.dev_ids = dids.data(); out.dev_off = doff.data(); out.dev_groups = dgrp.data();
+    int32_t rc = kxpu_classify(ctx_, recs.data(), n, &out);
+    if (rc != KXPU_OK) return kxfail(ctx_, "kxpu_classify", rc);  // fatal: there is no CPU path
+    for (uint32_t g = 0; g < out.n_groups; g++) {
+        std::vector<NvidiaGpuDevice> devs;
+        for (uint32_t k = goff[g]; k < goff[g + 1]; k++) {
+            uint32_t i = gmem[k];
+            devs.push_back(NvidiaGpuDevice{std::string(recs[i].bdf), accept[i]});  // :171-174
+        }
+        iommuMap.emplace_back(std::to_string(gids[g]), std::move(devs));
+    }
+    for (uint32_t d = 0; d < out.n_devids; d++) {
+        std::vector<std::string> groups;
+        for (uint32_t k = doff[d]; k < doff[d + 1]; k++) groups.push_back(std::to_string(dgrp[k]));  // :169
+        deviceMap.emplace_back(devIdString(dids[d]), std::move(groups));
+    }
+    return Error();
+}
+
+Error Plugin::ensureTable() {
+    if (table_) return Error();
+    FILE *f = fopen(pciIdsFilePath.c_str(), "rb");  // device_plugin.go:210
+    if (!f) return fail("Error opening pci ids file " + pciIdsFilePath);
+    std::vector<uint8_t> text;
+    uint8_t buf[1 << 16];
+    size_t k;
+    while ((k = fread(buf, 1, sizeof buf, f)) > 0) text.insert(text.end(), buf, buf + k);
+    fclose(f);
+    int32_t rc = kxpu_pciids_load(ctx_, text.data(), text.size(), &table_);
+    if (rc != KXPU_OK) { table_ = nullptr; return kxfail(ctx_, "kxpu_pciids_load", rc); }
+    return Error();
+}
+
+static bool parseHex4(const std::string &s, uint32_t &v) {
+    if (s.size() != 4) return false;
+    v = 0;
+    for (char c : s) {
+        uint32_t d;
+        if (c >= '0' && c <= '9') d = (uint32_t)(c - '0');
+        else if (c >= 'a' && c <= 'f') d = (uint32_t)(c - 'a' + 10);
+        else return false;
+        v = v * 16 + d;
+    }
+    return true;
+}
+
+// getDeviceName, device_plugin.go:208-259.  "" means "not found" exactly like the reference;
+// sysfs ids are four lowercase hex digits, anything else is treated as not found.
+std::string Plugin::getDeviceName(const std::string &deviceID) {
+    Error e = ensureTable();
+    if (e) { fprintf(stderr, "%s\n", e.message.c_str()); return ""; }  // :211-214
+    uint32_t d;
+    if (!parseHex4(deviceID, d)) return "";
+    uint32_t key = (0x10deu << 16) | d;  // nvidiaVendorID, :19
+    int32_t row = KXPU_ROW_MISS;
+    if (kxpu_lookup(ctx_, table_, &key, 1, &row) != KXPU_OK || row == KXPU_ROW_MISS) {
+        fprintf(stderr, "Could not find NVIDIA device with id: %s\n", deviceID.c_str());  // :234
+        return "";
+    }
+    uint8_t name[65536];
+    uint32_t offs[2];
+    size_t need = 0;
+    if (kxpu_names(ctx_, table_, &row, 1, name, sizeof name, offs, &need) != KXPU_OK) return "";
+    return std::string((const char *)name, need);
+}
+
+// generateCDISpec, device_plugin.go:55-80 + CdiSpec.Save, cdi/spec.go:85-127
+Error Plugin::generateCDISpec(const OrderedMap<std::vector<NvidiaGpuDevice>> &m, const std::string &format) {
+    std::vector<kxpu_cdidev> devs;
+    for (const auto &kv : m) {
+        for (const NvidiaGpuDevice &dev : kv.second) {
+            kxpu_cdidev c;
+            memset(&c, 0, sizeof c);
+            strncpy(c.bdf, dev.addr.c_str(), sizeof c.bdf - 1);
+            c.iommu_group = (uint32_t)strtoul(kv.first.c_str(), nullptr, 10);
+            c.index = dev.index;
+            devs.push_back(c);
+        }
+    }
+    // Go ranges over the map in random order (:59); canonical order = ascending index
+    std::sort(devs.begin(), devs.end(), [](const kxpu_cdidev &a, const kxpu_cdidev &b) { return a.index < b.index; });
+    const int32_t fmt = format == "YAML" ? KXPU_FMT_YAML : KXPU_FMT_JSON;  // spec.go:86-89,102-114
+    size_t len = 0;
+    int32_t rc = kxpu_cdi_emit(ctx_, fmt, devs.data(), devs.size(), nullptr, 0, &len);
+    if (rc != KXPU_OK && rc != KXPU_E_NOSPACE) return kxfail(ctx_, "kxpu_cdi_emit", rc);
+    std::vector<uint8_t> doc(len ? len : 1);
+    rc = kxpu_cdi_emit(ctx_, fmt, devs.data(), devs.size(), doc.data(), len, &len);
+    if (rc != KXPU_OK) return kxfail(ctx_, "kxpu_cdi_emit", rc);
+    const std::string file_path = cdiConfigPath + "cdi-vfio-xxxx" + (fmt == KXPU_FMT_YAML ? ".yaml" : ".json");  // :79, spec.go:92
+    FILE *f = fopen(file_path.c_str(), "wb");  // os.Create
+    if (!f) {
+        printf("Error creating file: %s\n", strerror(errno));  // spec.go:95: printed and swallowed
+        return Error();
+    }
+    size_t w = fwrite(doc.data(), 1, len, f);
+    fclose(f);
+    if (w != len) { printf("Error writing to file\n"); return Error(); }
+    lastCdiFile = file_path;
+    printf("Data successfully written to file\n");  // spec.go:126
+    return Error();
+}
+
+// createDevicePlugins, device_plugin.go:83-112 (nothing is started: no gRPC here)
+Error Plugin::createDevicePlugins() {
+    devicePlugins.clear();
+    for (const auto &kv : deviceMap) {  // :91
+        GenericDevicePlugin dp;
+        for (const std::string &dev : kv.second) dp.devs.push_back(Device{dev, kHealthy});  // :93-98
+        std::string devpluginName = getDeviceName(kv.first);                                // :99
+        if (devpluginName.empty()) {
+            fprintf(stderr, "Error: Could not find device name for device id: %s\n", kv.first.c_str());
+            devpluginName = kv.first;  // :100-103
+        }
+        dp.devpluginName = devpluginName;
+        dp.devicePath = "/dev/vfio/";                                                          // :105
+        dp.socketPath = std::string(kDevicePluginPath) + "kata-xpu-" + devpluginName + ".sock";  // generic:76
+        devicePlugins.push_back(std::move(dp));
+    }
+    return Error();
+}
+
+Error Plugin::InitiateDevicePlugin() {
+    Error e = createIommuDeviceMap();  // :46
+    if (e) return e;
+    e = generateCDISpec(iommuMap);  // :49
+    if (e) return e;
+    return createDevicePlugins();  // :52
+}
+
+// the Trim half of readIDFromFileFunc (:189) for the Allocate re-validation, which compares one
+// freshly read vendor file per allocated device (generic_device_plugin.go:334)
+static std::string trimID(const std::string &raw) {
+    if (raw.size() < 2) return std::string();
+    size_t a = 2, b = raw.size();
+    while (a < b && raw[a] == '\n') a++;
+    while (b > a && raw[b - 1] == '\n') b--;
+    return raw.substr(a, b - a);
+}
+
+// Allocate, generic_device_plugin.go:320-355, for one ContainerAllocateRequest
+Error Plugin::Allocate(const std::vector<std::string> &devicesIDs, ContainerAllocateResponse &resp) {
+    std::vector<uint64_t> devIndexes;
+    const auto &returnedMap = returnIommuMap();
+    for (const std::string &iommuId : devicesIDs) {  // :324
+        const std::vector<NvidiaGpuDevice> *nvDevs = nullptr;
+        for (const auto &kv : returnedMap) if (kv.first == iommuId) { nvDevs = &kv.second; break; }
+        if (!nvDevs) continue;  // unknown group id: empty nvDevs, no error (:327)
+        for (const NvidiaGpuDevice &dev : *nvDevs) {
+            std::string iommuGroup, vendor;
+            if (!readLink(basePath, dev.addr, "iommu_group", iommuGroup) || iommuGroup != iommuId)  // :329-333
+                return fail("invalid allocation request: unknown device: " + dev.addr);
+            if (!readIDFromFile(basePath, dev.addr, "vendor", vendor) || trimID(vendor) != "10de")  // :334-338
+                return fail("invalid allocation request: unknown device: " + dev.addr);
+            devIndexes.push_back(dev.index);  // :340
+        }
+    }
+    resp.CDIDevices.clear();
+    if (!devIndexes.empty()) {  // updateResponseForCDI :274-299; strategy cdi-cri is on (:61)
+        std::vector<uint32_t> offs(devIndexes.size() + 1);
+        std::vector<uint8_t> buf(36 * devIndexes.size());
+        size_t need = 0;
+        int32_t rc = kxpu_alloc_names(ctx_, devIndexes.data(), devIndexes.size(), buf.data(), buf.size(), offs.data(), &need);
+        if (rc != KXPU_OK) return fail("failed to get allocate response: " + std::string(kxpu_strerror(rc)));
+        for (size_t i = 0; i < devIndexes.size(); i++)
+            resp.CDIDevices.emplace_back((const char *)buf.data() + offs[i], offs[i + 1] - offs[i]);
+    }
+    resp.Envs.clear();
+    resp.Envs[kK8SCDIVendorClass] = kCdiVendorClass;  // :348-350 overwrites Envs
+    return Error();
+}
+
+Error Plugin::ListAndWatchBytes(const GenericDevicePlugin &dp, std::vector<uint8_t> &out) {
+    std::vector<uint32_t> groups;
+    std::vector<uint8_t> healthy;
+    for (const Device &d : dp.devs) {
+        groups.push_back((uint32_t)strtoul(d.ID.c_str(), nullptr, 10));
+        healthy.push_back(d.Health == kHealthy);
+    }
+    size_t len = 0;
+    int32_t rc = kxpu_lw_encode(ctx_, groups.data(), healthy.data(), groups.size(), nullptr, 0, &len);
+    if (rc != KXPU_OK && rc != KXPU_E_NOSPACE) return kxfail(ctx_, "kxpu_lw_encode", rc);
+    out.resize(len);
+    if (len == 0) return Error();
+    rc = kxpu_lw_encode(ctx_, groups.data(), healthy.data(), groups.size(), out.data(), len, &len);
+    if (rc != KXPU_OK) return kxfail(ctx_, "kxpu_lw_encode", rc);
+    return Error();
+}
+
+}  // namespace device_plugin
+
+// ----------------------------------------------------------------------------------------
+// C surface for the Python tests (tests/test_host*.py): drives the class above the way
+// cmd/main.go drives the Go package.
+// ----------------------------------------------------------------------------------------
+using device_plugin::Plugin;
+
+static void jstr(std::string &o, const std::string &s) {
+    o += '"';
+    for (char c : s) { if (c == '"' || c == '\\') o += '\\'; o += c; }
+    o += '"';
+}
+
+static int copy_out(const std::string &s, char *out, size_t cap) {
+    if (s.size() + 1 > cap) return -1;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+extern "C" {
+
+// CPU only: the raw gather of createIommuDeviceMap (no GPU involved)
+int kxh_gather(const char *base_path, kxpu_devrec *out, size_t cap, size_t *n, char *err, size_t errcap) {
+    Plugin p(nullptr);
+    p.basePath = base_path;
+    std::vector<kxpu_devrec> recs;
+    device_plugin::Error e = p.gatherRecords(recs);
+    if (e) { copy_out(e.message, err, errcap); return -1; }
+    *n = recs.size();
+    if (recs.size() > cap) return -2;
+    memcpy(out, recs.data(), recs.size() * sizeof(kxpu_devrec));
+    return 0;
+}
+
+void *kxh_new(kxpu_ctx *ctx, const char *base_path, const char *pciids_path, const char *cdi_dir) {
+    Plugin *p = new Plugin(ctx);
+    p->basePath = base_path;
+    p->pciIdsFilePath = pciids_path;
+    p->cdiConfigPath = cdi_dir;
+    return p;
+}
+void kxh_free(void *h) { delete (Plugin *)h; }
+
+// InitiateDevicePlugin + a JSON dump of the resulting state
+int kxh_init(void *h, const char *format, char *json, size_t cap) {
+    Plugin *p = (Plugin *)h;
+    device_plugin::Error e = p->createIommuDeviceMap();
+    if (!e) e = p->generateCDISpec(p->iommuMap, format);
+    if (!e) e = p->createDevicePlugins();
+    if (e) { copy_out(e.message, json, cap); return -1; }
+    std::string o = "{\"iommuMap\":[";
+    bool first = true;
+    for (const auto &kv : p->iommuMap) {
+        if (!first) o += ',';
+        first = false;
+        o += '['; jstr(o, kv.first); o += ",[";
+        for (size_t i = 0; i < kv.second.size(); i++) {
+            if (i) o += ',';
+            o += '['; jstr(o, kv.second[i].addr); o += ',' + std::to_string(kv.second[i].index) + ']';
+        }
+        o += "]]";
+    }
+    o += "],\"deviceMap\":[";
+    first = true;
+    for (const auto &kv : p->deviceMap) {
+        if (!first) o += ',';
+        first = false;
+        o += '['; jstr(o, kv.first); o += ",[";
+        for (size_t i = 0; i < kv.second.size(); i++) { if (i) o += ','; jstr(o, kv.second[i]); }
+        o += "]]";
+    }
+    o += "],\"plugins\":[";
+    first = true;
+    for (const auto &dp : p->devicePlugins) {
+        if (!first) o += ',';
+        first = false;
+        o += "{\"name\":"; jstr(o, dp.devpluginName);
+        o += ",\"resource\":"; jstr(o, "nvidia.com/" + dp.devpluginName);
+        o += ",\"socket\":"; jstr(o, dp.socketPath);
+        o += ",\"devs\":[";
+        for (size_t i = 0; i < dp.devs.size(); i++) {
+            if (i) o += ',';
+            o += '['; jstr(o, dp.devs[i].ID); o += ','; jstr(o, dp.devs[i].Health); o += ']';
+        }
+        o += "]}";
+    }
+    o += "],\"cdiFile\":"; jstr(o, p->lastCdiFile); o += '}';
+    return copy_out(o, json, cap);
+}
+
+// Allocate for one container request; ids = comma separated IOMMU group ids
+int kxh_allocate(void *h, const char *ids_csv, char *json, size_t cap) {
+    Plugin *p = (Plugin *)h;
+    std::vector<std::string> ids;
+    std::string cur;
+    for (const char *c = ids_csv; *c; c++) { if (*c == ',') { ids.push_back(cur); cur.clear(); } else cur += *c; }
+    if (!cur.empty() || (ids_csv[0] && ids_csv[strlen(ids_csv) - 1] == ',')) ids.push_back(cur);
+    device_plugin::ContainerAllocateResponse resp;
+    device_plugin::Error e = p->Allocate(ids, resp);
+    if (e) { copy_out(e.message, json, cap); return -1; }
+    std::string o = "{\"envs\":{";
+    bool first = true;
+    for (const auto &kv : resp.Envs) { if (!first) o += ','; first = false; jstr(o, kv.first); o += ':'; jstr(o, kv.second); }
+    o += "},\"cdi_devices\":[";
+    for (size_t i = 0; i < resp.CDIDevices.size(); i++) { if (i) o += ','; jstr(o, resp.CDIDevices[i]); }
+    o += "]}";
+    return copy_out(o, json, cap);
+}
+
+int kxh_list_and_watch(void *h, int plugin_index, uint8_t *out, size_t cap) {
+    Plugin *p = (Plugin *)h;
+    if (plugin_index < 0 || (size_t)plugin_index >= p->devicePlugins.size()) return -1;
+    std::vector<uint8_t> b;
+    if (p->ListAndWatchBytes(p->devicePlugins[(size_t)plugin_index], b)) return -1;
+    if (b.size() > cap) return -2;
+    memcpy(out, b.data(), b.size());
+    return (int)b.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// device_plugin.hpp -- host side of the discovery hot path, above the C ABI (include/kxpu.h).
+//
+// The reference host is Go; this image has no Go toolchain, so the host logic that sits
+// above libkxpu.so is written in C++ and mirrors the reference's package
+// pkg/device_plugin one to one: same function names, same package-level seams
+// (basePath, pciIdsFilePath, readLink, readIDFromFile -- device_plugin.go:36-39,
+// returnIommuMap -- generic_device_plugin.go:34), same argument meaning, same error
+// behaviour ("log and degrade": unreadable entries are skipped, an unknown device id
+// falls back to the raw id, an Allocate re-validation failure is an error naming the bdf).
+// The syscalls (walk, read, readlink) stay on the host exactly where the reference does
+// them; everything per-device / per-byte after that goes through the kxpu_* calls.
+// The gRPC server itself (Register / ListAndWatch stream / Allocate handler plumbing,
+// generic_device_plugin.go:128-220) is out of scope and stays in the Go binary; the Go
+// cgo shim that replaces this file in production is shown in INTEGRATION.md.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/kxpu.h"
+
+namespace device_plugin {
+
+// pkg/device_plugin/device_plugin.go:24-28
+struct NvidiaGpuDevice {
+    std::string addr;  // PCI address of device
+    uint64_t index;    // PCI device index on PCI bus
+};
+
+// Go maps iterate in random order; the canonical order used here (and by the oracle) is
+// first-seen walk order, which is one of the orders the reference can produce.
+template <typename V>
+using OrderedMap = std::vector<std::pair<std::string, V>>;
+
+// pkg/device_plugin/generic_device_plugin.go:35-48 (the fields the hot path touches)
+struct Device {  // pluginapi.Device
+    std::string ID;
+    std::string Health;
+};
+struct GenericDevicePlugin {
+    std::string devpluginName;   // resource name suffix: "nvidia.com/<devpluginName>" (:211)
+    std::string socketPath;      // DevicePluginPath + "kata-xpu-<name>.sock" (:76)
+    std::string devicePath;      // "/dev/vfio/" (device_plugin.go:105)
+    std::vector<Device> devs;
+};
+
+// pluginapi.ContainerAllocateResponse as Allocate fills it (generic_device_plugin.go:304-350)
+struct ContainerAllocateResponse {
+    std::map<std::string, std::string> Envs;
+    std::vector<std::string> CDIDevices;  // CDIDevice{Name}
+};
+
+struct Error {
+    bool failed = false;
+    std::string message;
+    explicit operator bool() const { return failed; }
+};
+
+class Plugin {
+  public:
+    // ---- seams (device_plugin.go:36-39, generic_device_plugin.go:34)
+    std::string basePath = "/sys/bus/pci/devices";
+    std::string pciIdsFilePath = "/usr/pci.ids";
+    std::string cdiConfigPath = "/var/run/cdi/";  // device_plugin.go:20
+    std::function<bool(const std::string &base, const std::string &addr, const std::string &link, std::string &out)> readLink;
+    std::function<bool(const std::string &base, const std::string &addr, const std::string &prop, std::string &out)> readIDFromFile;
+    std::function<const OrderedMap<std::vector<NvidiaGpuDevice>> &()> returnIommuMap;
+
+    // ---- state (device_plugin.go:31,34)
+    OrderedMap<std::vector<NvidiaGpuDevice>> iommuMap;  // group id -> devices
+    OrderedMap<std::vector<std::string>> deviceMap;     // device id -> iommu groups
+    std::vector<GenericDevicePlugin> devicePlugins;
+    std::string lastCdiFile;
+
+    explicit Plugin(kxpu_ctx *ctx);
+    ~Plugin();
+
+    // device_plugin.go:44-53 without the blocking gRPC part
+    Error InitiateDevicePlugin();
+    // device_plugin.go:126-180: walk + raw gather on the host, classify on the GPU (S1)
+    Error createIommuDeviceMap();
+    // device_plugin.go:208-259: parse-once table + batched lookup + sanitiser on the GPU (S2)
+    std::string getDeviceName(const std::string &deviceID);
+    // device_plugin.go:55-80 + cdi/spec.go:85-127: emit on the GPU, host writes the file (S3)
+    Error generateCDISpec(const OrderedMap<std::vector<NvidiaGpuDevice>> &m, const std::string &format = "YAML");
+    // device_plugin.go:83-112: per device id device lists + plugin objects (S4); nothing is started
+    Error createDevicePlugins();
+    // generic_device_plugin.go:320-355 for one container request (S5)
+    Error Allocate(const std::vector<std::string> &devicesIDs, ContainerAllocateResponse &resp);
+    // generic_device_plugin.go:224: the bytes of ListAndWatchResponse{Devices: dpi.devs}
+    Error ListAndWatchBytes(const GenericDevicePlugin &dp, std::vector<uint8_t> &out);
+
+    // raw gather only (no GPU): exposed for CPU tests of the walk
+    Error gatherRecords(std::vector<kxpu_devrec> &recs);
+
+  private:
+    kxpu_ctx *ctx_;
+    kxpu_table *table_ = nullptr;
+    Error ensureTable();
+};
+
+}  // namespace device_plugin
