@@ -5,6 +5,7 @@
 
 #include "pciids.cu"  // kernels (single translation unit keeps them inlinable and static)
 #include "pciids2.cu"
+#include "pciids3.cu"
 
 #include <cstdlib>
 
@@ -73,8 +74,11 @@ extern "C" int32_t kxpu_ctx_create(int32_t ordinal, kxpu_ctx **out) {
                          (int)sizeof(kxparse::ParseSmem));
     cudaFuncSetAttribute(kxparse2::parse_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(sizeof(kxparse2::WarpSmem) * kxparse2::WARPS));
-    const char *pv = getenv("KXPU_PARSE_V");  // 1 = CTA-tiled kernel (pciids.cu), 2 = warp-autonomous (default)
-    c->parse_version = (pv && pv[0] == '1') ? 1 : 2;
+    cudaFuncSetAttribute(kxparse3::parse_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(kxparse3::CtaSmem3));
+    // 1 = CTA-tiled kernel (pciids.cu), 2 = warp-autonomous (pciids2.cu), 3 = super-chunk (pciids3.cu, default)
+    const char *pv = getenv("KXPU_PARSE_V");
+    c->parse_version = (pv && pv[0] >= '1' && pv[0] <= '3') ? pv[0] - '0' : 3;
     *out = c;
     return KXPU_OK;
 }
@@ -269,6 +273,15 @@ static int parse_grid_v2(kxpu_ctx *ctx, uint32_t num_chunks) {
     return (int)(g < 1 ? 1 : g);
 }
 
+static int parse_grid_v3(kxpu_ctx *ctx, uint32_t num_sc) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kxparse3::parse_kernel_v3, kxparse2::NT, sizeof(kxparse3::CtaSmem3));
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)per_sm * ctx->sm_count;
+    if (g > (long long)num_sc) g = num_sc;
+    return (int)(g < 1 ? 1 : g);
+}
+
 static int32_t launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n,
                                unsigned long long base, int check_valid) {
     kxparse::FinalizeParams F;
@@ -292,18 +305,24 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
         return KXPU_E_INVALID;
     }
     if (base + n >= (1ull << 44)) return KXPU_E_UNSUPPORTED;
-    const bool v2 = ctx->parse_version == 2;
-    const uint32_t tile_bytes = v2 ? (uint32_t)kxparse2::CW : (uint32_t)kxparse::T;
-    const uint32_t num_tiles = (uint32_t)((n + tile_bytes - 1) / tile_bytes);
+    int version = ctx->parse_version;
     uint32_t cap = 1u << 16;
     uint32_t blob_cap = (uint32_t)std::min<size_t>(std::max<size_t>(n, 256), 4u << 20);
     for (int attempt = 0; attempt < 8; attempt++) {
         kxpu_table *t = nullptr;
+        const uint32_t tile_bytes = version == 1 ? (uint32_t)kxparse::T : (uint32_t)kxparse2::CW;
+        const uint32_t num_tiles = (uint32_t)((n + tile_bytes - 1) / tile_bytes);
+        const uint32_t num_sc = (num_tiles + kxparse3::SCC - 1) / kxparse3::SCC;
         int32_t rc = table_alloc(ctx, cap, blob_cap, num_tiles, &t);
         if (rc != KXPU_OK) return rc;
         if (num_tiles > 0) {
             KxTimer tm(ctx, KXPU_T_PARSE);
-            if (v2) {
+            if (version == 3) {
+                kxparse3::Params3 P;
+                P.text = d_text; P.n = n; P.base = base; P.num_chunks = num_tiles; P.num_sc = num_sc;
+                P.sc_state = t->tile_state; P.tab = t->dev; P.carry_in = carry_in;
+                kxparse3::parse_kernel_v3<<<parse_grid_v3(ctx, num_sc), kxparse2::NT, sizeof(kxparse3::CtaSmem3), ctx->stream>>>(P);
+            } else if (version == 2) {
                 kxparse2::Params P;
                 P.text = d_text; P.n = n; P.base = base; P.num_chunks = num_tiles;
                 P.chunk_state = t->tile_state; P.tab = t->dev; P.carry_in = carry_in;
@@ -345,6 +364,13 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
             if (rc != KXPU_OK) { table_release(ctx, t); return rc; }
             cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
             KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        if (ctx->h_ctl[KX_C_PEND_OVERFLOW]) {
+            // more than PENDCAP device lines of one 64 KiB super-chunk are governed by an earlier
+            // super-chunk (lines shorter than ~30 bytes): the warp-autonomous kernel has no such limit
+            table_release(ctx, t);
+            version = 2;
+            continue;
         }
         if (ctx->h_ctl[KX_C_OVERFLOW]) {
             table_release(ctx, t);

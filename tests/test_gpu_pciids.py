@@ -105,6 +105,18 @@ def test_long_block_needs_tile_lookback(kx, oracle):
     check_text(kx, oracle, text, extra_keys=[0xabcd0000, 0xabcd4e1f, 0xabce0001, 0xabcd4e20])
 
 
+def test_short_lines_in_huge_block(kx, oracle):
+    """> 2048 device lines of one 64 KiB super-chunk governed by an EARLIER super-chunk: the v3
+    kernel's parking buffer overflows and the library falls back to the v2 kernel."""
+    lines = [b"abcd  Big\n"] + [b"\t%04x  x\n" % (d & 0xffff) for d in range(40000)] + [b"abce  N\n\t0001  n\n"]
+    text = b"".join(lines)
+    assert len(text) > 5 * 65536
+    check_text(kx, oracle, text, extra_keys=[0xabcd0000, 0xabcd9c3f, 0xabcdffff, 0xabce0001])
+    # every line a bare newline / tiny: more line starts than the per-warp list holds (multi-window path)
+    text = b"10de  NV\n" + b"\n".join(b"\t%04x" % d for d in range(3000)) + b"\n\n\n\n" * 3000 + b"\t0001  late\n"
+    check_text(kx, oracle, text, extra_keys=[0x10de0000, 0x10de0bb7, 0x10de0001])
+
+
 def test_too_long_line(kx, oracle):
     ok_line = b"#" + b"x" * 65534
     bad_line = b"#" + b"x" * 65535
