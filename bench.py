@@ -97,7 +97,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": "warm-up + timed region, 100 ms period"}
 
 
 def host_threads():
@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--settle-steps", type=int, default=400, help="untimed extra warm-up steps (clock settling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -225,13 +226,17 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step().free()
-    parse_ms, fin_ms, merge_ms, look_ms = [], [], [], []
-    barrier()
+    # clocks are sampled from before the warm-up to the end of the timed region (the timed region
+    # alone, K x ~1 ms, is shorter than nvidia-smi's sampling period)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step().free()
+    for _ in range(args.settle_steps):  # ~0.5 s of untimed steps: clocks settle and nvidia-smi gets samples (same count on all ranks)
+        step().free()
+    parse_ms, fin_ms, merge_ms, look_ms = [], [], [], []
+    barrier()
     launches0 = kx.launch_count()
     kx.timer_begin()
     t_wall = time.time()
@@ -305,7 +310,7 @@ def main():
                           "lookup": float(np.mean(look_ms))},
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "kxparse::parse_kernel",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "kxparse3::parse_kernel_v3",
                          "algorithmic_bytes_per_launch": n},
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(n + 4 * NQ),
                     "d2h_bytes_per_step": int(4 * NQ), "ms_per_step": e2e_step},

@@ -6,6 +6,7 @@
 #include "pciids.cu"  // kernels (single translation unit keeps them inlinable and static)
 #include "pciids2.cu"
 #include "pciids3.cu"
+#include "slab.cuh"
 
 #include <cstdlib>
 
@@ -352,6 +353,12 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
         fprintf(stderr, "[kxpu dbg] lookbacks %u poll %u sleep_unready_near %u hops %u sleep_noprefix %u\n", ctx->h_ctl[8],
                 ctx->h_ctl[9], ctx->h_ctl[10], ctx->h_ctl[11], ctx->h_ctl[12]);
 #endif
+        if (!check_valid && ctx->h_ctl[KX_C_LONGLINE_HINT]) {
+            // sharded load: the shard's bufio.ErrTooLong cut-off travels in the slab header
+            kxparse::trunc_kernel<<<1, 1024, 0, ctx->stream>>>(d_text, n, base, t->dev.trunc);
+            KX_LAUNCHED(ctx);
+            KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
         if (ctx->h_ctl[KX_C_NEED_TRUNC] == 2u) {
             // a >= 1 KiB stretch without a line start was seen: compute the exact
             // bufio.ErrTooLong cut-off and finalize again.
@@ -391,6 +398,149 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
     }
     return KXPU_E_CAPACITY;
 }
+
+// ------------------------------------------------------------------ sharded load: merge side
+namespace kxmerge {
+using namespace kxcomm;
+
+// every gathered candidate row / vendor row folds into the merged table with the parse rule
+__global__ void __launch_bounds__(256) merge_insert_kernel(const uint8_t *gather, int R, size_t stride, SlabCaps caps,
+                                                           KxTableDev tab) {
+    const uint32_t per = caps.rows > caps.vendors ? caps.rows : caps.vendors;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(t / per);
+    const uint32_t i = (uint32_t)(t % per);
+    if (r >= R) return;
+    const uint8_t *slab = gather + (size_t)r * stride;
+    const SlabHeader *h = reinterpret_cast<const SlabHeader *>(slab);
+    if (i == 0 && h->trunc != KX_NO_OFF) atomicMin(tab.trunc, h->trunc);
+    if (i < h->n_rows) {
+        const SlabRow row = reinterpret_cast<const SlabRow *>(slab + slab_rows_off())[i];
+        kxparse2::table_fold(tab, row.key, row.line, row.anchor);
+    }
+    if (i < h->n_vendors) {
+        const SlabVendor v = reinterpret_cast<const SlabVendor *>(slab + slab_vendors_off(caps))[i];
+        atomicMin(&tab.vendor_first[v.vendor & 0xffffu], v.first);
+    }
+}
+
+__global__ void __launch_bounds__(256) merge_finalize_kernel(KxTableDev tab, int32_t *row_of_slot, uint32_t *row_key,
+                                                             unsigned long long *row_line, unsigned long long *row_anchor,
+                                                             uint32_t *row_name_off, uint32_t *row_name_len) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot > tab.cap) return;
+    const unsigned long long line = tab.min_line[slot];
+    const uint32_t key = slot == tab.cap ? KX_EMPTY_KEY : tab.keys[slot];
+    int32_t row = -1;
+    if (line != KX_NO_OFF && !(slot < tab.cap && key == KX_EMPTY_KEY)) {
+        const unsigned long long anchor = tab.min_anchor[slot];
+        if (anchor == tab.vendor_first[key >> 16] && line < *tab.trunc) {
+            row = (int32_t)atomicAdd(&tab.counters[KX_C_NROWS], 1u);
+            row_key[row] = key; row_line[row] = line; row_anchor[row] = anchor;
+            row_name_off[row] = 0; row_name_len[row] = 0;
+        }
+    }
+    row_of_slot[slot] = row;
+}
+
+// the winning row's name stays where the all-gather put it: record its offset in the gather buffer
+__global__ void __launch_bounds__(256) merge_names_kernel(const uint8_t *gather, int R, size_t stride, SlabCaps caps,
+                                                          KxTableDev tab, const int32_t *row_of_slot,
+                                                          uint32_t *row_name_off, uint32_t *row_name_len) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(t / caps.rows);
+    const uint32_t i = (uint32_t)(t % caps.rows);
+    if (r >= R) return;
+    const uint8_t *slab = gather + (size_t)r * stride;
+    const SlabHeader *h = reinterpret_cast<const SlabHeader *>(slab);
+    if (i >= h->n_rows) return;
+    const SlabRow row = reinterpret_cast<const SlabRow *>(slab + slab_rows_off())[i];
+    uint32_t slot;
+    if (row.key == KX_EMPTY_KEY) slot = tab.cap;
+    else {
+        slot = kx_hash(row.key) >> tab.shift;
+        for (uint32_t step = 0; step < tab.cap; step++) {
+            const uint32_t k = tab.keys[slot];
+            if (k == row.key) break;
+            if (k == KX_EMPTY_KEY) return;
+            slot = (slot + 1) & (tab.cap - 1);
+        }
+    }
+    const int32_t out = row_of_slot[slot];
+    if (out >= 0 && tab.min_line[slot] == row.line) {
+        row_name_off[out] = (uint32_t)((size_t)r * stride + slab_blob_off(caps) + row.name_off);
+        row_name_len[out] = row.name_len;
+    }
+}
+}  // namespace kxmerge
+
+int32_t kx_table_from_gather(kxpu_ctx *ctx, void *d_gather, int R, size_t stride, kxcomm::SlabCaps caps, kxpu_table **out) {
+    using namespace kxcomm;
+    // headers first: a capacity overflow on any rank makes every rank retry with larger slabs
+    std::vector<SlabHeader> hdr((size_t)R);
+    for (int r = 0; r < R; r++)
+        cudaMemcpyAsync(&hdr[(size_t)r], (const uint8_t *)d_gather + (size_t)r * stride, sizeof(SlabHeader), cudaMemcpyDeviceToHost,
+                        ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        KX_SET_ERR(ctx, "all-gather failed: %s", cudaGetErrorString(e));
+        cudaFreeAsync(d_gather, ctx->stream);
+        return KXPU_E_CUDA;
+    }
+    size_t total_rows = 0;
+    for (int r = 0; r < R; r++) {
+        if (hdr[(size_t)r].overflow) { cudaFreeAsync(d_gather, ctx->stream); return KXPU_E_CAPACITY; }
+        total_rows += hdr[(size_t)r].n_rows;
+    }
+    if ((size_t)R * stride >= 0xFFFFFFFFull) { cudaFreeAsync(d_gather, ctx->stream); return KXPU_E_UNSUPPORTED; }
+    uint32_t cap = 1u << 16;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        kxpu_table *t = nullptr;
+        int32_t rc = table_alloc(ctx, cap, 16, 1, &t);
+        if (rc != KXPU_OK) { cudaFreeAsync(d_gather, ctx->stream); return rc; }
+        const uint32_t per = caps.rows > caps.vendors ? caps.rows : caps.vendors;
+        const size_t nthreads = (size_t)R * per;
+        kxmerge::merge_insert_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t *)d_gather, R, stride,
+                                                                                                caps, t->dev);
+        kxmerge::merge_finalize_kernel<<<(cap + 1 + 255) / 256, 256, 0, ctx->stream>>>(t->dev, t->row_of_slot, t->row_key, t->row_line,
+                                                                                     t->row_anchor, t->row_name_off, t->row_name_len);
+        kxmerge::merge_names_kernel<<<(unsigned)(((size_t)R * caps.rows + 255) / 256), 256, 0, ctx->stream>>>(
+            (const uint8_t *)d_gather, R, stride, caps, t->dev, t->row_of_slot, t->row_name_off, t->row_name_len);
+        ctx->launches += 3;
+        cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            KX_SET_ERR(ctx, "merge failed: %s", cudaGetErrorString(e));
+            table_release(ctx, t);
+            cudaFreeAsync(d_gather, ctx->stream);
+            return KXPU_E_CUDA;
+        }
+        if (ctx->h_ctl[KX_C_OVERFLOW]) {
+            table_release(ctx, t);
+            if (cap >= (1u << 28)) { cudaFreeAsync(d_gather, ctx->stream); return KXPU_E_CAPACITY; }
+            cap <<= 2;
+            continue;
+        }
+        t->n_rows = ctx->h_ctl[KX_C_NROWS];
+        t->gather = d_gather;               // names are served from the gathered slabs
+        t->blob = (uint8_t *)d_gather;
+        t->blob_cap = (uint32_t)((size_t)R * stride);
+        *out = t;
+        return KXPU_OK;
+    }
+    cudaFreeAsync(d_gather, ctx->stream);
+    return KXPU_E_CAPACITY;
+}
+
+void kx_table_local_view(kxpu_table *t, KxTableDev *dev, uint32_t *cap, uint32_t *n_rows, uint32_t *blob_used,
+                         const uint32_t **row_key, const unsigned long long **row_line, const unsigned long long **row_anchor,
+                         const uint32_t **row_name_off, const uint32_t **row_name_len, const uint8_t **blob) {
+    *dev = t->dev; *cap = t->cap; *n_rows = t->n_rows; *blob_used = t->blob_used;
+    *row_key = t->row_key; *row_line = t->row_line; *row_anchor = t->row_anchor;
+    *row_name_off = t->row_name_off; *row_name_len = t->row_name_len; *blob = t->blob;
+}
+
+void kx_table_release(kxpu_ctx *ctx, kxpu_table *t) { table_release(ctx, t); }
 
 extern "C" int32_t kxpu_pciids_load_device(kxpu_ctx *ctx, const void *d_text, size_t n, kxpu_table **out) {
     KX_ENTER(ctx);
