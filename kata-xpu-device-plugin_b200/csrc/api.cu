@@ -349,10 +349,6 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
             table_release(ctx, t);
             return KXPU_E_CUDA;
         }
-#ifdef KX_DEBUG_COUNTERS
-        fprintf(stderr, "[kxpu dbg] lookbacks %u poll %u sleep_unready_near %u hops %u sleep_noprefix %u\n", ctx->h_ctl[8],
-                ctx->h_ctl[9], ctx->h_ctl[10], ctx->h_ctl[11], ctx->h_ctl[12]);
-#endif
         if (!check_valid && ctx->h_ctl[KX_C_LONGLINE_HINT]) {
             // sharded load: the shard's bufio.ErrTooLong cut-off travels in the slab header
             kxparse::trunc_kernel<<<1, 1024, 0, ctx->stream>>>(d_text, n, base, t->dev.trunc);

@@ -22,11 +22,6 @@
 
 namespace kxparse2 {
 
-#ifdef KX_DEBUG_COUNTERS
-#define KX_DBG(i) do { if (lane == 0) atomicAdd(&P.tab.counters[i], 1u); } while (0)
-#else
-#define KX_DBG(i) do { } while (0)
-#endif
 
 constexpr int CW = 2048;                 // chunk bytes per warp iteration
 constexpr int HALF = 1024;
@@ -172,21 +167,17 @@ __device__ __forceinline__ void table_fold(const KxTableDev &tb, uint32_t key, u
 // s_first = status words of chunks g-1-lane loaded earlier by the caller (0 if not loaded).
 __device__ __forceinline__ unsigned long long lookback(const Params &P, uint32_t g, uint32_t lane,
                                                        unsigned long long s_first) {
-#ifdef KX_NO_LOOKBACK  // timing experiment only: wrong results
-    return 0;
-#endif
     long long top = (long long)g - 1;
     unsigned long long s = s_first;
     bool fresh = false;
     if (g > 0 && (__shfl_sync(0xffffffffu, s_first, 0) & ST_MASK) == 0ull) {
         // the direct predecessor has not published yet: one lane polls, the others sleep
         if (lane == 0) {
-            while ((ld_volatile_u64(&P.chunk_state[g - 1]) & ST_MASK) == 0ull) { KX_DBG(9); __nanosleep(1000); }
+            while ((ld_volatile_u64(&P.chunk_state[g - 1]) & ST_MASK) == 0ull) __nanosleep(1000);
         }
         __syncwarp();
         fresh = true;
     }
-    KX_DBG(8);
     for (;;) {
         const long long idx = top - (long long)lane;
         if (fresh) s = idx >= 0 ? ld_volatile_u64(&P.chunk_state[idx]) : (ST_PREFIX | P.carry_in);
@@ -197,13 +188,11 @@ __device__ __forceinline__ unsigned long long lookback(const Params &P, uint32_t
         if (pm) {
             const uint32_t f = (uint32_t)__ffs((int)pm) - 1u;
             if ((zm & ((1u << f) - 1u)) == 0u) return __shfl_sync(0xffffffffu, s, (int)f) & ~ST_MASK;
-            KX_DBG(10);
         } else if (zm == 0u) {
             top -= 32;  // 32 chunks without any top-level line: look further back
             fresh = true;
-            KX_DBG(11);
             continue;
-        } else { KX_DBG(12); }
+        }
         __nanosleep(200);  // a predecessor has not published yet: yield the issue slots
         fresh = true;
     }
