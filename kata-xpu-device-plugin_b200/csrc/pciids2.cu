@@ -93,13 +93,14 @@ __device__ __forceinline__ uint32_t lop3_nor_and(uint32_t a, uint32_t b, uint32_
 }
 
 // 16-bit mask of the bytes of v that equal '\n' (bit b = byte b).  Per word: the exact
-// zero-byte test on x^0x0a.. (3 ops), then IDP.4A gathers the four 0x80 flags, weighted
+// zero-byte test on y = x^0x0a..: t = (y & 0x7f..) + 0x7f..; flag = ~(t | y) & 0x80.. -- bit 7 of
+// y equals bit 7 of x (0x0a has it clear), so x itself feeds the last LOP3 (3 ops), then IDP.4A gathers the four 0x80 flags, weighted
 // 1,2,4,8 (or 16..128), straight into the accumulator.
 __device__ __forceinline__ uint32_t nl_mask16(const uint4 v, uint32_t k7f, uint32_t k0a, uint32_t k80) {
-    uint32_t f0 = lop3_nor_and(lop3_and_xor(v.x, k7f, k0a) + k7f, v.x ^ k0a, k80);
-    uint32_t f1 = lop3_nor_and(lop3_and_xor(v.y, k7f, k0a) + k7f, v.y ^ k0a, k80);
-    uint32_t f2 = lop3_nor_and(lop3_and_xor(v.z, k7f, k0a) + k7f, v.z ^ k0a, k80);
-    uint32_t f3 = lop3_nor_and(lop3_and_xor(v.w, k7f, k0a) + k7f, v.w ^ k0a, k80);
+    uint32_t f0 = lop3_nor_and(lop3_and_xor(v.x, k7f, k0a) + k7f, v.x, k80);
+    uint32_t f1 = lop3_nor_and(lop3_and_xor(v.y, k7f, k0a) + k7f, v.y, k80);
+    uint32_t f2 = lop3_nor_and(lop3_and_xor(v.z, k7f, k0a) + k7f, v.z, k80);
+    uint32_t f3 = lop3_nor_and(lop3_and_xor(v.w, k7f, k0a) + k7f, v.w, k80);
     uint32_t lo = __dp4a(f0, 0x08040201u, 0u);
     lo = __dp4a(f1, 0x80402010u, lo);
     uint32_t hi = __dp4a(f2, 0x08040201u, 0u);

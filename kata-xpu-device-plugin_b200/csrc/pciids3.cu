@@ -15,7 +15,7 @@
 //     (device id + position, 4 B each) and folded one super-chunk iteration later, after one
 //     warp resolved the carry with a decoupled look-back over per-SUPER-CHUNK status words in
 //     global memory (32x fewer words, a whole iteration of slack);
-//   * three __syncthreads per 64 KiB.
+//   * one split barrier (mbarrier arrive / wait) per 64 KiB.
 #pragma once
 #include "common.cuh"
 #include "pciids2.cu"  // nl_mask16, hex4_swar, table_fold, TMA/mbarrier helpers, CV_*/ST_* encodings
@@ -61,6 +61,7 @@ struct CtaSmem3 {
     uint32_t sc_q[3];                             // super-chunk tickets: [k % 3] = iteration k, [(k+1) % 3] = k + 1
     uint32_t pub_cnt[2];
     uint32_t fold_cnt[2];
+    alignas(8) unsigned long long iter_bar;       // mbarrier: one arrival per warp per iteration
 };
 
 struct Params3 {
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
         C.sc_q[1] = atomicAdd(&P.tab.counters[KX_C_TICKET], 1u);
         C.pend_cnt[0] = C.pend_cnt[1] = C.pend_cnt[2] = 0;
         C.pub_cnt[0] = C.pub_cnt[1] = 0;
+        mbar_init(&C.iter_bar, WARPS);
         C.fold_cnt[0] = C.fold_cnt[1] = 0;
     }
     if (lane == 0) {
@@ -215,13 +217,19 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
     unsigned long long pf = 0;      // warp 0: status words of the super-chunks before sc_m1
     uint32_t k = 0;
     for (;; k++) {
-        const uint32_t sc = C.sc_q[k % 3u], sc_next = C.sc_q[(k + 1u) % 3u];
+        // The iteration boundary is a SPLIT barrier (mbarrier): a warp arrives when it has parsed
+        // its chunks of iteration k and only waits for the others' arrival where iteration k + 1
+        // first touches CTA-shared buffers (parking / folding), i.e. after the newline masks,
+        // classification, scan and publication of its first chunk.
+        const uint32_t sc = C.sc_q[k % 3u];
         if (sc >= P.num_sc) break;
+        uint32_t sc_next = 0;
         const uint32_t pb = k % 3u;
-        if (threadIdx.x == 0) {
-            C.sc_q[(k + 2u) % 3u] = atomicAdd(&P.tab.counters[KX_C_TICKET], 1u);  // ticket of iteration k + 2
-            C.pub_cnt[(k + 1u) & 1u] = 0;
-        }
+        auto iter_sync = [&]() {
+            if (k >= 1u) mbar_wait(&C.iter_bar, (k - 1u) & 1u);  // everybody finished iteration k - 1
+            if (threadIdx.x == 0) C.sc_q[(k + 2u) % 3u] = atomicAdd(&P.tab.counters[KX_C_TICKET], 1u);  // ticket of iteration k + 2
+            sc_next = C.sc_q[(k + 1u) % 3u];
+        };
         if (w == 0 && k >= 1u) {
             const long long idx = (long long)sc_m1 - 1 - (long long)lane;
             pf = idx >= 0 ? ld_volatile_u64(&P.sc_state[idx]) : 0ull;
@@ -276,6 +284,8 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
                     const uint32_t ma = nl_mask16(va, k7f, k0a, k80), mb = nl_mask16(vb, k7f, k0a, k80);
                     uint32_t mm = swz ? (mb | (ma << 16)) : (ma | (mb << 16));
                     rawnl |= mm;
+                    // a line start at o + 1 + b is real only below n_rel (ragged last chunk)
+                    if (n_rel <= (uint32_t)CW) mm &= n_rel > o + 1u ? (n_rel - o - 1u >= 32u ? 0xffffffffu : ((1u << (n_rel - o - 1u)) - 1u)) : 0u;
                     // classify the line that starts after each newline by its first two bytes:
                     //   neither '#' nor '\t': top-level line -- ends the vendor block
                     //     (device_plugin.go:229-236), the only kind locateVendor can match (:265)
@@ -287,9 +297,8 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
                         const uint32_t bit = mm & (0u - mm);
                         mm ^= bit;
                         const uint32_t c0 = lp[b], c1 = lp[b + 1u];
-                        const bool real = o + 1u + b < n_rel;
-                        const bool top = real && c0 != (uint32_t)'#' && c0 != (uint32_t)'\t';
-                        const bool cand = real && c0 == (uint32_t)'\t' && c1 != (uint32_t)'\t';
+                        const bool top = c0 != (uint32_t)'#' && c0 != (uint32_t)'\t';
+                        const bool cand = c0 == (uint32_t)'\t' && c1 != (uint32_t)'\t';
                         if (top) tm |= bit;
                         if (top || cand) km |= bit;
                     }
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
                 }
                 // 2 KiB without a newline may belong to a >= 64 KiB line (bufio.ErrTooLong): raise the
                 // hint, the exact cut-off is then computed by trunc_kernel (never for real pci.ids)
-                if (n_rel > (uint32_t)CW && !__any_sync(0xffffffffu, rawnl != 0u) && lane == 0)
+                if (n_rel > (uint32_t)CW && __reduce_or_sync(0xffffffffu, rawnl) == 0u && lane == 0)
                     atomicOr(&P.tab.counters[KX_C_LONGLINE_HINT], 1u);
                 const uint32_t cnt = (uint32_t)__popc(kh[0]) | ((uint32_t)__popc(kh[1]) << 16);
                 uint32_t incl = cnt;
@@ -357,9 +366,13 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
                         } else if (lane == 0) {
                             st_volatile_u64(&P.sc_state[sc], ST_NONE);
                         }
-                        if (lane == 0) C.agg_none[pb] = hm ? 0u : 1u;  // read one iteration later, after barrier #1
+                        if (lane == 0) {
+                            C.agg_none[pb] = hm ? 0u : 1u;  // read one iteration later
+                            C.pub_cnt[k & 1u] = 0;          // next used two iterations from now
+                        }
                     }
                 }
+                if (j == 0u) iter_sync();
 
                 // ------------------------------------------------------ one lane per kept line
                 uint32_t cP = P_NONE;  // governing top-level line so far; P_NONE = before the chunk's first one
@@ -428,7 +441,9 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
                     }
                     __syncwarp();
                 }
-            }  // c < nsc
+            } else if (j == 0u) {
+                iter_sync();
+            }
 
             // prefetch the chunk two steps ahead of this warp into the stage just released
             if (lane == 0) {
@@ -438,11 +453,13 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
             if (j == 1u && k >= 2u) fold_share(sc_m2, (k - 2u) % 3u, k & 1u);
         }
         if (w == 0 && k >= 1u) resolve_carry(sc_m1, (k - 1u) % 3u, (k - 1u) & 1u, pf);
-        __syncthreads();  // the one barrier per super-chunk
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&C.iter_bar)) : "memory");
         sc_m2 = sc_m1;
         sc_m1 = sc;
     }
     // drain: k iterations were run
+    if (k >= 1u) mbar_wait(&C.iter_bar, (k - 1u) & 1u);
     if (k >= 2u) fold_share(sc_m2, (k - 2u) % 3u, k & 1u);
     if (k >= 1u) {
         if (w == 0) {
