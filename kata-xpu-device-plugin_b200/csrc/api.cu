@@ -22,6 +22,7 @@ struct kxpu_table {
     unsigned long long *row_anchor = nullptr;
     uint32_t *row_name_off = nullptr;
     uint32_t *row_name_len = nullptr;
+    uint32_t *sel = nullptr;
     uint8_t *blob = nullptr;
     uint32_t blob_cap = 0;
     uint32_t n_rows = 0;
@@ -220,6 +221,7 @@ static int32_t table_alloc(kxpu_ctx *ctx, uint32_t cap, uint32_t blob_cap, uint3
     size_t o_row_anchor = off;  off = align_up(off + slots * 8, 256);
     size_t o_row_noff = off;    off = align_up(off + slots * 4, 256);
     size_t o_row_nlen = off;    off = align_up(off + slots * 4, 256);
+    size_t o_sel = off;         off = align_up(off + slots * 4, 256);
     size_t o_blob = off;        off = align_up(off + blob_cap, 256);
     t->arena_bytes = off;
     cudaError_t e = cudaMallocAsync(&t->arena, off, ctx->stream);
@@ -245,6 +247,7 @@ static int32_t table_alloc(kxpu_ctx *ctx, uint32_t cap, uint32_t blob_cap, uint3
     t->row_anchor = (unsigned long long *)(b + o_row_anchor);
     t->row_name_off = (uint32_t *)(b + o_row_noff);
     t->row_name_len = (uint32_t *)(b + o_row_nlen);
+    t->sel = (uint32_t *)(b + o_sel);
     t->blob = b + o_blob;
     t->blob_cap = blob_cap;
     cudaMemsetAsync(b, 0xff, ff_bytes, ctx->stream);
@@ -288,11 +291,12 @@ static int32_t launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_te
     kxparse::FinalizeParams F;
     F.text = d_text; F.n = n; F.base = base; F.tab = t->dev;
     F.row_of_slot = t->row_of_slot; F.row_key = t->row_key; F.row_line = t->row_line; F.row_anchor = t->row_anchor;
-    F.row_name_off = t->row_name_off; F.row_name_len = t->row_name_len;
+    F.row_name_off = t->row_name_off; F.row_name_len = t->row_name_len; F.sel = t->sel;
     F.blob = t->blob; F.blob_cap = t->blob_cap; F.check_valid = check_valid;
-    unsigned blocks = (t->cap + 1 + kxparse::FIN_WARPS - 1) / kxparse::FIN_WARPS;
-    kxparse::finalize_kernel<<<blocks, kxparse::FIN_WARPS * 32, 0, ctx->stream>>>(F);
-    KX_LAUNCHED(ctx);
+    kxparse::finalize_select_kernel<<<(t->cap + 1 + 255) / 256, 256, 0, ctx->stream>>>(F);
+    // one warp per selected slot; warps beyond the (device-side) count exit at once
+    kxparse::finalize_kernel<<<(t->cap + 1 + kxparse::FIN_WARPS - 1) / kxparse::FIN_WARPS, kxparse::FIN_WARPS * 32, 0, ctx->stream>>>(F);
+    ctx->launches += 2;
     KX_CUDA(ctx, cudaGetLastError());
     return KXPU_OK;
 }
@@ -363,6 +367,7 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
             uint32_t one = 1;
             cudaMemcpyAsync(&t->dev.counters[KX_C_NEED_TRUNC], &one, 4, cudaMemcpyHostToDevice, ctx->stream);
             cudaMemsetAsync(&t->dev.counters[KX_C_NROWS], 0, 12, ctx->stream);  // NROWS, BLOB_CURSOR, BLOB_OVERFLOW
+            cudaMemsetAsync(&t->dev.counters[KX_C_NSEL], 0, 4, ctx->stream);
             rc = launch_finalize(ctx, t, d_text, n, base, check_valid);
             if (rc != KXPU_OK) { table_release(ctx, t); return rc; }
             cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -387,7 +392,7 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
             blob_cap = (uint32_t)std::min<size_t>(n, (size_t)blob_cap * 8);
             continue;
         }
-        t->n_rows = ctx->h_ctl[KX_C_NROWS];
+        t->n_rows = ctx->h_ctl[KX_C_NSEL];  // row handle = index of the slot in the selection
         t->blob_used = ctx->h_ctl[KX_C_BLOB_CURSOR];
         *out = t;
         return KXPU_OK;

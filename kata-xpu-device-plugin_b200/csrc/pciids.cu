@@ -469,67 +469,112 @@ struct FinalizeParams {
     unsigned long long *row_anchor;
     uint32_t *row_name_off;
     uint32_t *row_name_len;
+    uint32_t *sel;  // [cap+1] valid slots (stage 1 -> stage 2)
     uint8_t *blob;
     uint32_t blob_cap;
     int check_valid;  // 1: apply vendor_first / trunc validity (single shard); 0: emit every local row (sharded)
 };
 
-// One warp per table slot: validity, row handle, sanitised name into the blob.
-__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const FinalizeParams F) {
-    __shared__ uint8_t s_buf[FIN_WARPS][NAME_BUF + 32];
-    const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5;
-    const uint32_t slot = blockIdx.x * FIN_WARPS + wl;
-    if (slot > F.tab.cap) return;
+// Stage 1, one thread per table slot: validity; valid slots are compacted into F.sel.
+__global__ void __launch_bounds__(256) finalize_select_kernel(const FinalizeParams F) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (F.tab.counters[KX_C_LONGLINE_HINT] != 0u && F.tab.counters[KX_C_NEED_TRUNC] == 0u && F.check_valid) {
         // the exact ErrTooLong cut-off has not been computed yet: ask the host to run
         // trunc_kernel and call finalize again.
-        if (slot == 0 && lane == 0) F.tab.counters[KX_C_NEED_TRUNC] = 2u;
+        if (slot == 0) F.tab.counters[KX_C_NEED_TRUNC] = 2u;
         return;
     }
-    const unsigned long long line = F.tab.min_line[slot];
-    const uint32_t key = slot == F.tab.cap ? KX_EMPTY_KEY : F.tab.keys[slot];
-    if (line == KX_NO_OFF || (slot < F.tab.cap && key == KX_EMPTY_KEY)) {
-        if (lane == 0) F.row_of_slot[slot] = -1;
-        return;
+    bool valid = false;
+    if (slot <= F.tab.cap) {
+        const unsigned long long line = F.tab.min_line[slot];
+        const uint32_t key = slot == F.tab.cap ? KX_EMPTY_KEY : F.tab.keys[slot];
+        valid = line != KX_NO_OFF && !(slot < F.tab.cap && key == KX_EMPTY_KEY);
+        if (valid && F.check_valid) valid = F.tab.min_anchor[slot] == F.tab.vendor_first[key >> 16] && line < *F.tab.trunc;
+        if (!valid) F.row_of_slot[slot] = -1;
     }
-    const unsigned long long anchor = F.tab.min_anchor[slot];
-    if (F.check_valid) {
-        const bool valid = anchor == F.tab.vendor_first[key >> 16] && line < *F.tab.trunc;
-        if (!valid) {
-            if (lane == 0) F.row_of_slot[slot] = -1;
-            return;
-        }
+    const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+    if (vm) {
+        uint32_t base = 0;
+        if ((threadIdx.x & 31u) == 0) base = atomicAdd(&F.tab.counters[KX_C_NSEL], (uint32_t)__popc(vm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (valid) F.sel[base + (uint32_t)__popc(vm & ((1u << (threadIdx.x & 31u)) - 1u))] = slot;
     }
-    // rest of the line after "\t" + 4 hex digits
-    const unsigned long long rs = line - F.base + 5ull;
+}
+
+// Stage 2, one warp per selected slot (row handle = index in F.sel): sanitised name into the
+// blob.  Blob space is claimed once per CTA (8 names) to keep the cursor atomic cheap.
+__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const FinalizeParams F) {
+    __shared__ uint8_t s_buf[FIN_WARPS][NAME_BUF + 32];
+    __shared__ uint32_t s_len[FIN_WARPS];
+    __shared__ uint32_t s_base;
+    const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5;
+    const uint32_t nsel = F.tab.counters[KX_C_NSEL];
+    const uint32_t si = blockIdx.x * FIN_WARPS + wl;
+    if (blockIdx.x * FIN_WARPS >= nsel) return;  // whole CTA idle
+    const bool active = si < nsel;
+    uint32_t slot = 0, key = 0, len = 0, start = 0, end = 0, out_len = 0;
+    unsigned long long line = 0, anchor = 0, rs = 0;
+    bool fast = false;
     uint8_t *buf = s_buf[wl];
-    uint32_t len = 0;
-    bool found = false;
-    for (uint32_t o = 0; o < (uint32_t)NAME_BUF + 32u && !found; o += 32u) {
-        unsigned long long pos = rs + o + lane;
-        uint32_t c = pos < F.n ? F.text[pos] : 0x0au;  // EOF terminates the last line
-        buf[o + lane] = (uint8_t)c;
-        uint32_t nlm = __ballot_sync(0xffffffffu, c == 0x0au);
-        if (nlm) { len = o + (uint32_t)__ffs((int)nlm) - 1u; found = true; }
-    }
-    __syncwarp();
-    uint32_t out_len = 0, out_off = 0;
-    if (found && len <= (uint32_t)NAME_BUF) {
-        if (len > 0 && buf[len - 1] == 0x0du) len--;  // bufio.ScanLines drops one trailing CR
-        uint32_t start = 0, end = 0;
-        if (lane == 0) trim_space(buf, len, start, end);
-        start = __shfl_sync(0xffffffffu, start, 0);
-        end = __shfl_sync(0xffffffffu, end, 0);
-        for (uint32_t o = start; o < end; o += 32u) {
-            uint32_t i = o + lane;
-            uint32_t ch = i < end ? sanitise_byte(buf, i, start, end) : 0u;
-            out_len += (uint32_t)__popc(__ballot_sync(0xffffffffu, ch != 0u));
+    if (active) {
+        slot = F.sel[si];
+        line = F.tab.min_line[slot];
+        key = slot == F.tab.cap ? KX_EMPTY_KEY : F.tab.keys[slot];
+        anchor = F.tab.min_anchor[slot];
+        rs = line - F.base + 5ull;  // rest of the line after "\t" + 4 hex digits
+        bool found = false;
+        for (uint32_t o = 0; o < (uint32_t)NAME_BUF + 32u && !found; o += 32u) {
+            unsigned long long pos = rs + o + lane;
+            uint32_t c = pos < F.n ? F.text[pos] : 0x0au;  // EOF terminates the last line
+            buf[o + lane] = (uint8_t)c;
+            uint32_t nlm = __ballot_sync(0xffffffffu, c == 0x0au);
+            if (nlm) { len = o + (uint32_t)__ffs((int)nlm) - 1u; found = true; }
         }
-        if (lane == 0) out_off = atomicAdd(&F.tab.counters[KX_C_BLOB_CURSOR], out_len);
-        out_off = __shfl_sync(0xffffffffu, out_off, 0);
-        if (out_off + out_len > F.blob_cap) {
-            if (lane == 0) F.tab.counters[KX_C_BLOB_OVERFLOW] = 1u;
+        __syncwarp();
+        fast = found && len <= (uint32_t)NAME_BUF;
+        if (fast) {
+            if (len > 0 && buf[len - 1] == 0x0du) len--;  // bufio.ScanLines drops one trailing CR
+            if (lane == 0) trim_space(buf, len, start, end);
+            start = __shfl_sync(0xffffffffu, start, 0);
+            end = __shfl_sync(0xffffffffu, end, 0);
+            for (uint32_t o = start; o < end; o += 32u) {
+                uint32_t i = o + lane;
+                uint32_t ch = i < end ? sanitise_byte(buf, i, start, end) : 0u;
+                out_len += (uint32_t)__popc(__ballot_sync(0xffffffffu, ch != 0u));
+            }
         } else {
+            // slow path: a name longer than the staging buffer (never in pci.ids): lane 0, serial,
+            // straight from global memory.
+            if (lane == 0) {
+                const uint8_t *g = F.text + rs;
+                unsigned long long avail = F.n - rs, l = 0;
+                while (l < avail && g[l] != 0x0au) l++;
+                len = (uint32_t)l;
+                if (len > 0 && g[len - 1] == 0x0du) len--;
+                trim_space(g, len, start, end);
+                for (uint32_t i = start; i < end; i++) out_len += sanitise_byte(g, i, start, end) != 0u;
+            }
+            out_len = __shfl_sync(0xffffffffu, out_len, 0);
+            start = __shfl_sync(0xffffffffu, start, 0);
+            end = __shfl_sync(0xffffffffu, end, 0);
+        }
+    }
+    if (lane == 0) s_len[wl] = out_len;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int k = 0; k < FIN_WARPS; k++) tot += s_len[k];
+        uint32_t base = tot ? atomicAdd(&F.tab.counters[KX_C_BLOB_CURSOR], tot) : 0u;
+        if (base + tot > F.blob_cap) { F.tab.counters[KX_C_BLOB_OVERFLOW] = 1u; base = 0xFFFFFFFFu; }
+        s_base = base;
+    }
+    __syncthreads();
+    if (!active) return;
+    uint32_t out_off = s_base;
+    const bool room = out_off != 0xFFFFFFFFu;
+    for (uint32_t k = 0; k < wl; k++) out_off += s_len[k];
+    if (room) {
+        if (fast) {
             uint32_t wr = out_off;
             for (uint32_t o = start; o < end; o += 32u) {
                 uint32_t i = o + lane;
@@ -538,40 +583,22 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const Finalize
                 if (ch) F.blob[wr + (uint32_t)__popc(bm & ((1u << lane) - 1u))] = (uint8_t)ch;
                 wr += (uint32_t)__popc(bm);
             }
-        }
-    } else {
-        // slow path: a name longer than the staging buffer (never in pci.ids): lane 0, serial,
-        // straight from global memory.
-        if (lane == 0) {
+        } else if (lane == 0) {
             const uint8_t *g = F.text + rs;
-            unsigned long long avail = F.n - rs, l = 0;
-            while (l < avail && g[l] != 0x0au) l++;
-            uint32_t ll = (uint32_t)l;
-            if (ll > 0 && g[ll - 1] == 0x0du) ll--;
-            uint32_t start, end;
-            trim_space(g, ll, start, end);
-            for (uint32_t i = start; i < end; i++) out_len += sanitise_byte(g, i, start, end) != 0u;
-            out_off = atomicAdd(&F.tab.counters[KX_C_BLOB_CURSOR], out_len);
-            if (out_off + out_len > F.blob_cap) F.tab.counters[KX_C_BLOB_OVERFLOW] = 1u;
-            else {
-                uint32_t wr = out_off;
-                for (uint32_t i = start; i < end; i++) {
-                    uint32_t ch = sanitise_byte(g, i, start, end);
-                    if (ch) F.blob[wr++] = (uint8_t)ch;
-                }
+            uint32_t wr = out_off;
+            for (uint32_t i = start; i < end; i++) {
+                uint32_t ch = sanitise_byte(g, i, start, end);
+                if (ch) F.blob[wr++] = (uint8_t)ch;
             }
         }
-        out_len = __shfl_sync(0xffffffffu, out_len, 0);
-        out_off = __shfl_sync(0xffffffffu, out_off, 0);
     }
     if (lane == 0) {
-        uint32_t row = atomicAdd(&F.tab.counters[KX_C_NROWS], 1u);
-        F.row_of_slot[slot] = (int32_t)row;
-        F.row_key[row] = key;
-        F.row_line[row] = line;
-        F.row_anchor[row] = anchor;
-        F.row_name_off[row] = out_off;
-        F.row_name_len[row] = out_len;
+        F.row_of_slot[slot] = (int32_t)si;
+        F.row_key[si] = key;
+        F.row_line[si] = line;
+        F.row_anchor[si] = anchor;
+        F.row_name_off[si] = room ? out_off : 0u;
+        F.row_name_len[si] = room ? out_len : 0u;
     }
 }
 
