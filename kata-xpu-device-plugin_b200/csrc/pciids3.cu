@@ -125,13 +125,14 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
     // chunks [0, tma_limit) can be staged with one bulk copy of STG_BYTES (no read past the text)
     const uint32_t tma_limit = P.n >= (unsigned long long)STG_BYTES ? (uint32_t)((P.n - STG_BYTES) / CW) + 1u : 0u;
     auto chunk_tma_ok = [&](uint32_t g) { return g < tma_limit; };
+    const unsigned long long pol = l2_evict_first_policy();
     // lane 0: start the TMA copy of chunk c of super-chunk scn into stage s (if it exists)
     auto issue = [&](uint32_t scn, uint32_t c, int s) {
         if (scn >= P.num_sc) return;
         const uint32_t g = scn * SCC + c;
         if (g < P.num_chunks && chunk_tma_ok(g)) {
             mbar_expect_tx(&S.bar[s], STG_BYTES);
-            tma_load_1d(S.stage[s], P.text + (unsigned long long)g * CW, STG_BYTES, &S.bar[s]);
+            tma_load_1d_stream(S.stage[s], P.text + (unsigned long long)g * CW, STG_BYTES, &S.bar[s], pol);
         }
     };
     if (lane == 0) {

@@ -134,3 +134,36 @@ def test_lw_encode_health(kx, oracle):
     h = (rng.random(5000) < 0.7).astype(np.uint8)
     assert kx.lw_encode(g, h) == oracle.lw_encode(g, h)
     assert kx.lw_encode(g[:0]) == b""
+
+
+def test_ctx_is_thread_safe(kx, oracle, pci_text):
+    """grpc-go runs Allocate handlers concurrently on one shared ctx (generic_device_plugin.go:320):
+    hammer one kxpu_ctx from several OS threads with the three per-request calls."""
+    import threading
+    tab = kx.pciids_load(pci_text)
+    want_names, _ = oracle.alloc_names(np.arange(64, dtype=np.uint64))
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for _ in range(40):
+                idx = rng.integers(0, 1 << 40, 64, dtype=np.uint64)
+                got, _ = kx.alloc_names(idx)
+                assert got == oracle.alloc_names(idx)[0]
+                rows = kx.lookup(tab, np.array([0x10de2330, 0x10de2901, 0x80861572], np.uint32))
+                assert rows[0] >= 0 and rows[1] == -1 and rows[2] >= 0
+                assert kx.names(tab, rows)[0] == [b"GH100_H100_SXM5_80GB", b"", b"ETHERNET_CONTROLLER_X710_FOR_10GBE_SFP"]
+                g = rng.integers(0, 5000, 17).astype(np.uint32)
+                assert kx.lw_encode(g) == oracle.lw_encode(g)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    assert kx.alloc_names(np.arange(64, dtype=np.uint64))[0] == want_names
+    tab.free()
