@@ -216,3 +216,24 @@ def test_names_nospace_and_empty(kx, pci_text):
     assert rc == -4 and need.value == 20
     assert kx.lookup(tab, np.empty(0, np.uint32)).size == 0
     tab.free()
+
+
+def test_repeated_loads_are_deterministic(kx, pci_text, oracle_rows):
+    """The parse kernel hands work between warps through mbarriers, shared-memory status words
+    and atomics; run it many times on a text that spans thousands of super-chunks and demand
+    the identical table every time (scheduling differs from run to run)."""
+    n, copies = len(pci_text), 120
+    d_one = kx.dev_alloc(n)
+    kx.upload(d_one, np.frombuffer(pci_text, np.uint8))
+    d_big = kx.dev_alloc(n * copies)
+    kx.replicate(d_big, d_one, n, copies)
+    for it in range(30):
+        tab = kx.pciids_load_device(d_big, n * copies - (it % 7) * 1001)  # ragged ends too
+        keys, offs, rows = kx.table_export(tab)
+        if (it % 7) == 0:
+            assert np.array_equal(keys, oracle_rows["key"]) and np.array_equal(offs, oracle_rows["line_off"]), it
+        else:
+            assert len(keys) == len(oracle_rows) and np.array_equal(offs, oracle_rows["line_off"]), it
+        tab.free()
+    kx.dev_free(d_big)
+    kx.dev_free(d_one)
