@@ -195,6 +195,9 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
                 cc.key_hi = ((uint32_t)(carry >> 44) & 0xffffu) << 16;
                 cc.valid = ((carry & CV_HAS_TOP) && (carry & CV_VOK)) ? 1u : 0u;
             }
+            // same pruning as in the per-line pass: a governing line that is not the first of its
+            // vendor id cannot produce a hit
+            if (cc.valid && P.tab.vendor_first[cc.key_hi >> 16] < cc.anchor) cc.valid = 0u;
             C.ccarry[cb][lane] = cc;
         }
         if (lane == 0) {
@@ -405,18 +408,24 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v3(const Params3 P) {
                         uint32_t val;
                         const bool ok = hex4_swar(lds_u32_unaligned(st, p + (istop ? 0u : 1u)), val);
                         const bool isdev = act && !istop && ok;
-                        const uint32_t myP = (ok ? 0x80000000u : 0u) | (val << 15) | p;
+                        const unsigned long long line_g = cbase + p;
+                        // A top-level line is a candidate vendor anchor; only the FIRST line with this
+                        // prefix counts (:265).  If an earlier one is already known, this block can
+                        // never produce a hit (a hit needs min_anchor == vendor_first): its device
+                        // lines are dropped right here instead of being folded into the table.
+                        bool alive = ok;
+                        if (istop && ok) {
+                            const unsigned long long vf = P.tab.vendor_first[val];
+                            if (line_g < vf) atomicMin(&P.tab.vendor_first[val], line_g);
+                            alive = line_g <= vf;
+                        }
+                        const uint32_t myP = (alive ? 0x80000000u : 0u) | (val << 15) | p;
                         const uint32_t tm = __ballot_sync(0xffffffffu, istop);
                         const uint32_t prev = tm & lt_mask;
                         const uint32_t g_src = __shfl_sync(0xffffffffu, myP, prev ? 31 - __clz((int)prev) : 0);
                         const uint32_t gov = prev ? g_src : cP;
                         const bool was_head = cP == P_NONE;
                         if (tm) cP = __shfl_sync(0xffffffffu, myP, 31 - __clz((int)tm));
-                        const unsigned long long line_g = cbase + p;
-                        if (istop && ok) {
-                            // candidate vendor anchor: only the first line with this prefix counts (:265)
-                            if (line_g < P.tab.vendor_first[val]) atomicMin(&P.tab.vendor_first[val], line_g);
-                        }
                         if (was_head) {
                             // device lines before the chunk's first top-level line are governed by an
                             // earlier chunk: park them (resolve_prev folds them one iteration later)
