@@ -74,6 +74,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
             : "memory");
     } while (!ok);
 }
+// same, but lets the hardware suspend the thread until the phase completes (or the hint expires):
+// a waiting warp does not compete for issue slots
+__device__ __forceinline__ void mbar_wait_suspend(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+            : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
