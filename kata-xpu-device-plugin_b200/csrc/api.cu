@@ -6,6 +6,7 @@
 #include "pciids.cu"  // kernels (single translation unit keeps them inlinable and static)
 #include "pciids2.cu"
 #include "pciids3.cu"
+#include "pciids4.cu"
 #include "slab.cuh"
 
 #include <cstdlib>
@@ -79,8 +80,10 @@ extern "C" int32_t kxpu_ctx_create(int32_t ordinal, kxpu_ctx **out) {
     cudaFuncSetAttribute(kxparse3::parse_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(kxparse3::CtaSmem3));
     // 1 = CTA-tiled kernel (pciids.cu), 2 = warp-autonomous (pciids2.cu), 3 = super-chunk (pciids3.cu, default)
+    cudaFuncSetAttribute(kxparse4::parse_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(kxparse4::CtaSmem4));
     const char *pv = getenv("KXPU_PARSE_V");
-    c->parse_version = (pv && pv[0] >= '1' && pv[0] <= '3') ? pv[0] - '0' : 3;
+    c->parse_version = (pv && pv[0] >= '1' && pv[0] <= '4') ? pv[0] - '0' : 4;
     *out = c;
     return KXPU_OK;
 }
@@ -213,7 +216,7 @@ static int32_t table_alloc(kxpu_ctx *ctx, uint32_t cap, uint32_t blob_cap, uint3
     size_t o_trunc = off;       off = align_up(off + 8, 256);
     size_t ff_bytes = off;
     size_t o_counters = off;    off = align_up(off + KX_C_COUNT * 4, 256);
-    size_t o_tiles = off;       off = align_up(off + (size_t)num_tiles * 8, 256);
+    size_t o_tiles = off;       off = align_up(off + ((size_t)num_tiles + 64) * 8, 256);
     size_t zero_bytes = off - ff_bytes;
     size_t o_row_of_slot = off; off = align_up(off + slots * 4, 256);
     size_t o_row_key = off;     off = align_up(off + slots * 4, 256);
@@ -286,6 +289,15 @@ static int parse_grid_v3(kxpu_ctx *ctx, uint32_t num_sc) {
     return (int)(g < 1 ? 1 : g);
 }
 
+static int parse_grid_v4(kxpu_ctx *ctx, uint32_t num_ranges) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kxparse4::parse_kernel_v4, kxparse2::NT, sizeof(kxparse4::CtaSmem4));
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)per_sm * ctx->sm_count;
+    if (g > (long long)num_ranges) g = num_ranges;
+    return (int)(g < 1 ? 1 : g);
+}
+
 static int32_t launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n,
                                unsigned long long base, int check_valid) {
     kxparse::FinalizeParams F;
@@ -322,7 +334,18 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
         if (rc != KXPU_OK) return rc;
         if (num_tiles > 0) {
             KxTimer tm(ctx, KXPU_T_PARSE);
-            if (version == 3) {
+            if (version == 4) {
+                kxparse4::Params4 P;
+                P.text = d_text; P.n = n; P.base = base; P.num_chunks = num_tiles;
+                P.num_sc = (num_tiles + kxparse4::SCC4 - 1) / kxparse4::SCC4;
+                P.num_ranges = (P.num_sc + kxparse4::RSC - 1) / kxparse4::RSC;
+                P.range_state = t->tile_state;                               // [num_ranges]
+                P.deferred = (uint32_t *)(t->tile_state + P.num_ranges);     // [num_tiles]
+                P.tab = t->dev; P.carry_in = carry_in;
+                kxparse4::parse_kernel_v4<<<parse_grid_v4(ctx, P.num_ranges), kxparse2::NT, sizeof(kxparse4::CtaSmem4), ctx->stream>>>(P);
+                KX_LAUNCHED(ctx);
+                kxparse4::resolve_deferred_kernel<<<2 * ctx->sm_count, kxparse4::RES_WARPS * 32, 0, ctx->stream>>>(P);
+            } else if (version == 3) {
                 kxparse3::Params3 P;
                 P.text = d_text; P.n = n; P.base = base; P.num_chunks = num_tiles; P.num_sc = num_sc;
                 P.sc_state = t->tile_state; P.tab = t->dev; P.carry_in = carry_in;

@@ -29,6 +29,7 @@
 #define KX_C_NEED_TRUNC 7
 #define KX_C_PEND_OVERFLOW 8
 #define KX_C_NSEL 9
+#define KX_C_DEFER 10
 #define KX_C_COUNT 16
 
 struct KxTableDev {

@@ -1,12 +1,13 @@
 """Aggregate ncu per-line instruction counts into user-given line regions: file:lo-hi:name ..."""
-import csv, subprocess, sys
+import csv, os, shlex, subprocess, sys
+EXTRA = shlex.split(os.environ.get("NCU_EXTRA", ""))  # e.g. NCU_EXTRA="-k regex:parse_kernel_v4"
 rep = sys.argv[1]
 regions = []
 for a in sys.argv[2:]:
     f, rng, name = a.split(":")
     lo, hi = rng.split("-")
     regions.append((f, int(lo), int(hi), name))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, *EXTRA, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 cur, hd, items = None, None, []
 for r in rows:

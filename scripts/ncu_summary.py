@@ -1,8 +1,9 @@
 """Summarise an .ncu-rep: key metrics + instruction share / stall samples per source line."""
-import csv, subprocess, sys
+import csv, os, shlex, subprocess, sys
+EXTRA = shlex.split(os.environ.get("NCU_EXTRA", ""))  # e.g. NCU_EXTRA="-k regex:parse_kernel_v4"
 rep = sys.argv[1]
 topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, *EXTRA, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
@@ -27,7 +28,7 @@ for i, h in enumerate(hdr):
                 print("%-70s %s" % (h, vals[i]))
         except ValueError:
             pass
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, *EXTRA, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 cur, hd, items = None, None, []
 for r in rows:
