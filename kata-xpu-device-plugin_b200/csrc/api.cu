@@ -7,6 +7,7 @@
 #include "pciids2.cu"
 #include "pciids3.cu"
 #include "pciids4.cu"
+#include "pciids5.cu"
 #include "slab.cuh"
 
 #include <cstdlib>
@@ -83,7 +84,9 @@ extern "C" int32_t kxpu_ctx_create(int32_t ordinal, kxpu_ctx **out) {
     cudaFuncSetAttribute(kxparse4::parse_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(kxparse4::CtaSmem4));
     const char *pv = getenv("KXPU_PARSE_V");
-    c->parse_version = (pv && pv[0] >= '1' && pv[0] <= '4') ? pv[0] - '0' : 4;
+    cudaFuncSetAttribute(kxparse5::parse_kernel_v5, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(kxparse5::WarpSmem5) * kxparse2::WARPS));
+    c->parse_version = (pv && pv[0] >= '1' && pv[0] <= '5') ? pv[0] - '0' : 5;
     *out = c;
     return KXPU_OK;
 }
@@ -334,7 +337,30 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
         if (rc != KXPU_OK) return rc;
         if (num_tiles > 0) {
             KxTimer tm(ctx, KXPU_T_PARSE);
-            if (version == 4) {
+            if (version == 5) {
+                kxparse5::Params5 P;
+                P.text = d_text; P.n = n; P.base = base; P.num_chunks = num_tiles;
+                P.tma_limit = n >= (size_t)kxparse2::STG_BYTES ? (uint32_t)((n - kxparse2::STG_BYTES) / kxparse2::CW) + 1u : 0u;
+                P.num_ranges = (num_tiles + kxparse5::RCH5 - 1) / kxparse5::RCH5;
+                P.range_state = t->tile_state;                            // [num_ranges]
+                P.range_carry = t->tile_state + P.num_ranges;             // [num_ranges]
+                P.lead = (uint32_t *)(t->tile_state + 2 * P.num_ranges);  // [num_ranges]
+                P.tasks = P.lead + P.num_ranges;                          // [num_tiles]
+                P.tab = t->dev; P.carry_in = carry_in;
+                int per_sm = 0;
+                const size_t smem = sizeof(kxparse5::WarpSmem5) * kxparse2::WARPS;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kxparse5::parse_kernel_v5, kxparse2::NT, smem);
+                if (per_sm < 1) per_sm = 1;
+                // persistent grid; every warp holds two range tickets at a time
+                uint32_t grid = (uint32_t)per_sm * ctx->sm_count;
+                const uint32_t need = (P.num_ranges + 2 * kxparse2::WARPS - 1) / (2 * kxparse2::WARPS);
+                if (grid > need) grid = need;
+                kxparse5::parse_kernel_v5<<<grid, kxparse2::NT, smem, ctx->stream>>>(P);
+                KX_LAUNCHED(ctx);
+                kxparse5::resolve_ranges_kernel<<<(P.num_ranges + 255u) / 256u, 256, 0, ctx->stream>>>(P);
+                KX_LAUNCHED(ctx);
+                kxparse5::resolve_chunks_kernel<<<4 * ctx->sm_count, kxparse5::RES_WARPS * 32, 0, ctx->stream>>>(P);
+            } else if (version == 4) {
                 kxparse4::Params4 P;
                 P.text = d_text; P.n = n; P.base = base; P.num_chunks = num_tiles;
                 P.num_sc = (num_tiles + kxparse4::SCC4 - 1) / kxparse4::SCC4;
@@ -342,6 +368,7 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
                 P.range_state = t->tile_state;                               // [num_ranges]
                 P.deferred = (uint32_t *)(t->tile_state + P.num_ranges);     // [num_tiles]
                 P.tab = t->dev; P.carry_in = carry_in;
+                P.tma_limit = n >= (size_t)kxparse2::STG_BYTES ? (uint32_t)((n - kxparse2::STG_BYTES) / kxparse2::CW) + 1u : 0u;
                 kxparse4::parse_kernel_v4<<<parse_grid_v4(ctx, P.num_ranges), kxparse2::NT, sizeof(kxparse4::CtaSmem4), ctx->stream>>>(P);
                 KX_LAUNCHED(ctx);
                 kxparse4::resolve_deferred_kernel<<<2 * ctx->sm_count, kxparse4::RES_WARPS * 32, 0, ctx->stream>>>(P);

@@ -1,0 +1,340 @@
+// pciids5.cu -- parse kernel v5 (default): warp-autonomous, alive-first, nothing waits.
+//
+// v4 (pciids4.cu) showed where the rest of the time went once dead blocks were skipped
+// (profiles/r01_parse_v4d_*): 8 % of all instructions were warps polling the CTA barrier that
+// orders the per-chunk status words, and the per-iteration bookkeeping of the shared ticket /
+// phase-B pipeline cost as much as the newline masks.  v5 removes the sharing:
+//   * the text is cut into RANGES of 8 chunks (16 KiB) handed out to WARPS by ticket (a static
+//     split leaves the SM half empty at the end: the issue arbiter favours some warps, they
+//     finish early); a warp streams its ranges 2 KiB at a time through a private 3-stage ring
+//     of 1-D TMA bulk copies (cp.async.bulk + mbarrier) -- no CTA barrier, no shared status;
+//   * per chunk: newline masks (SWAR + IDP.4A) and line classes, then the TOP-LEVEL lines only
+//     (hex prefix, vendor_first check/update -> alive bit).  A device line matters only under
+//     the FIRST line with its vendor id (device_plugin.go:265): lines under a dead line are
+//     dropped unparsed, lines under an alive one are folded by the lane that owns them;
+//   * lines in front of the chunk's first top-level line are governed by the carry the warp
+//     keeps in two registers along its range; at the start of a range the carry is not known
+//     (the range before belongs to another warp): the warp only counts how many leading chunks
+//     are affected (one word per range);
+//   * resolve_ranges_kernel: one thread per range walks back over the per-range status words
+//     (all published by then); only if the governing line is alive -- the first copy of a
+//     vendor block -- the leading chunks are queued, and resolve_chunks_kernel stages each of
+//     them again (one warp per chunk) and folds its head lines.
+// Results are exactly those of v1..v4 (same fold rule, same finalize).
+#pragma once
+#include "common.cuh"
+#include "pciids4.cu"  // shared-window helpers, chunk_masks, fold_lines, stage_chunk_manual
+#include "table.cuh"
+
+namespace kxparse5 {
+
+using namespace kxparse2;
+using kxparse4::chunk_masks;
+using kxparse4::fold_lines;
+using kxparse4::lds32_unaligned;
+using kxparse4::lds8;
+using kxparse4::mbar_expect_tx_a;
+using kxparse4::mbar_try_a;
+using kxparse4::stage_chunk_manual;
+using kxparse4::tma_load_a;
+
+constexpr int STAGES5 = 3;
+constexpr int RCH5 = 8;  // chunks per range (16 KiB)
+constexpr int RES_WARPS = 8;
+static_assert(RCH5 > STAGES5, "the prefetch cursor may run at most one range ahead");
+
+struct WarpSmem5 {
+    alignas(16) uint8_t stage[STAGES5][STG_BYTES];
+    alignas(8) unsigned long long bar[STAGES5];
+};
+
+struct Params5 {
+    const uint8_t *text;
+    unsigned long long n, base;
+    uint32_t num_chunks;
+    uint32_t tma_limit;               // chunks [0, tma_limit) can be staged with one bulk copy of STG_BYTES
+    uint32_t num_ranges;
+    unsigned long long *range_state;  // [num_ranges] inclusive carry at the end of the range (ST_*/CV_*)
+    uint32_t *lead;                   // [num_ranges] leading chunks whose head lines wait for the resolve kernels
+    unsigned long long *range_carry;  // [num_ranges] resolve: governing line at the start of an alive range
+    uint32_t *tasks;                  // [num_chunks] resolve: chunks to stage again, count in counters[KX_C_DEFER]
+    KxTableDev tab;
+    unsigned long long carry_in;
+};
+
+__global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    WarpSmem5 *W = reinterpret_cast<WarpSmem5 *>(smem_raw);
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    if (lane == 0) {
+        for (int s = 0; s < STAGES5; s++) mbar_init(&W[w].bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // two ranges in flight per warp: the current one and the next (its ticket is drawn one range early)
+    uint32_t tk = 0;
+    if (lane == 0) {
+        tk = atomicAdd(&P.tab.counters[KX_C_TICKET], 2u);
+    }
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    uint32_t r = tk, r_next = tk + 1u;
+    if (r >= P.num_ranges) return;
+
+    // shared-window addresses (see kxparse4::lds128)
+    const uint32_t a_stage0 = smem_u32(smem_raw) + w * (uint32_t)sizeof(WarpSmem5);  // stage s: + s * STG_BYTES
+    const uint32_t a_bar0 = a_stage0 + (uint32_t)offsetof(WarpSmem5, bar);           // bar s:   + 8 * s
+
+    uint32_t k7f = 0x7f7f7f7fu, k0a = 0x0a0a0a0au, k80 = 0x80808080u;
+    asm volatile("" : "+r"(k7f), "+r"(k0a), "+r"(k80));
+
+    const unsigned long long pol = l2_evict_first_policy();
+    auto issue = [&](uint32_t g, uint32_t s) {  // lane 0: start the TMA copy of chunk g into stage s
+        if (g < P.tma_limit) {
+            mbar_expect_tx_a(a_bar0 + 8u * s, STG_BYTES);
+            tma_load_a(a_stage0 + s * (uint32_t)STG_BYTES, P.text + (unsigned long long)g * CW, STG_BYTES, a_bar0 + 8u * s, pol);
+        }
+    };
+    if (lane == 0) {
+        issue(r * RCH5, 0);
+        issue(r * RCH5 + 1u, 1);
+        issue(r * RCH5 + 2u, 2);
+    }
+
+    uint32_t phase_bits = 0, s = 0;
+    for (;;) {
+        // ticket of the range after next; consumed (shuffled) late in this range
+        uint32_t tk2 = 0;
+        if (lane == 0) tk2 = atomicAdd(&P.tab.counters[KX_C_TICKET], 1u);
+        // carry along the range: the governing line at the start of the next chunk as a status word
+        // (LS_* of pciids3.cu; 0 = not known) plus the chunk that holds the line (0xffffffff = the
+        // shard's carry-in)
+        uint32_t rc_x = 0, rc_g = 0;
+        if (r == 0u) {
+            rc_x = LS_PUB | (((P.carry_in & CV_HAS_TOP) && (P.carry_in & CV_VOK)) ? (LS_TOP | LS_VOK) : 0u);
+            rc_g = 0xffffffffu;
+        }
+        uint32_t lead = r == 0u ? 0u : (uint32_t)RCH5;  // chunks whose head lines nobody can judge yet
+        const uint32_t gb = r * RCH5;
+        const uint32_t cnt = P.num_chunks - gb < (uint32_t)RCH5 ? P.num_chunks - gb : (uint32_t)RCH5;
+        for (uint32_t i = 0; i < cnt; i++) {
+            const uint32_t g = gb + i;
+            const uint32_t st = a_stage0 + s * (uint32_t)STG_BYTES;
+            const unsigned long long cbase = P.base + (unsigned long long)g * CW;
+            uint32_t n_rel = CW + 1;  // line starts at p < n_rel are real (p == CW: first byte of the next chunk)
+            if (g < P.tma_limit) {
+                const uint32_t bar = a_bar0 + 8u * s, par = (phase_bits >> s) & 1u;
+                while (!mbar_try_a(bar, par)) {
+                }
+                phase_bits ^= 1u << s;
+            } else {
+                n_rel = stage_chunk_manual(P.text, P.n, g, lane, W[w].stage[s]);
+            }
+
+            uint32_t kh[2], th[2], rawnl;
+            chunk_masks(st, lane, n_rel, k7f, k0a, k80, kh, th, rawnl);
+
+            // the shard starts with a line start at p = 0 (no newline before it)
+            uint32_t base_info = P_NONE;  // top-level line in front of the lane windows (only that one)
+            if (g == 0u && n_rel > 0u) {
+                const uint32_t c0 = lds8(st), c1 = lds8(st + 1u);
+                if (c0 != (uint32_t)'#' && c0 != (uint32_t)'\t') {
+                    uint32_t val;
+                    const bool ok = hex4_swar(lds32_unaligned(st), val);
+                    bool alive = ok;
+                    if (ok) {
+                        const unsigned long long vf = P.tab.vendor_first[val];
+                        if (lane == 0 && cbase < vf) atomicMin(&P.tab.vendor_first[val], cbase);
+                        alive = cbase <= vf;
+                    }
+                    base_info = (alive ? 0x80000000u : 0u) | ((ok ? val : 0u) << 15);
+                } else if (c0 == (uint32_t)'\t' && c1 != (uint32_t)'\t') {
+                    // device line at the very start: governed by the shard's carry-in, which is known
+                    uint32_t dv;
+                    if (lane == 0 && (P.carry_in & CV_HAS_TOP) && (P.carry_in & CV_VOK) && hex4_swar(lds32_unaligned(st + 1u), dv))
+                        table_fold(P.tab, (((uint32_t)(P.carry_in >> 44) & 0xffffu) << 16) | dv, cbase, P.carry_in & CV_ANCHOR_MASK);
+                }
+            }
+
+            // top-level lines, by the lane that owns them: a candidate vendor anchor; only the FIRST
+            // line with this prefix counts (:265).  If an earlier one is already known, this block
+            // can never produce a hit (a hit needs min_anchor == vendor_first): it is dead.
+            uint32_t linfo0 = P_NONE, linfo1 = P_NONE;  // last top-level line of my windows: alive<<31 | vendor<<15 | position
+            bool any_alive = base_info != P_NONE;
+            {
+                uint32_t t0 = th[0], t1 = th[1];
+                while (t0 | t1) {
+                    const bool second = t0 == 0u;
+                    const uint32_t tmv = second ? t1 : t0;
+                    const uint32_t bit = tmv & (0u - tmv);
+                    const uint32_t rest = tmv ^ bit;
+                    if (second) t1 = rest; else t0 = rest;
+                    const uint32_t pbase = (second ? (uint32_t)HALF : 0u) + lane * 32u + 1u;
+                    const uint32_t p = pbase + (31u - (uint32_t)__clz((int)bit));
+                    uint32_t val;
+                    const bool ok = hex4_swar(lds32_unaligned(st + p), val);
+                    const unsigned long long line_g = cbase + p;
+                    bool alive = ok;
+                    if (ok) {
+                        const unsigned long long vf = P.tab.vendor_first[val];
+                        if (line_g < vf) atomicMin(&P.tab.vendor_first[val], line_g);
+                        alive = line_g <= vf;
+                    }
+                    if (alive) {
+                        // device lines of my window between this line and the next top-level line
+                        const uint32_t nxt = rest & (0u - rest);
+                        const uint32_t seg = (second ? kh[1] & ~th[1] : kh[0] & ~th[0]) & ~(bit | (bit - 1u)) & (nxt ? nxt - 1u : 0xffffffffu);
+                        fold_lines(P.tab, st, cbase, seg, pbase, val << 16, line_g);
+                        any_alive = true;
+                    }
+                    const uint32_t info = (alive ? 0x80000000u : 0u) | ((ok ? val : 0u) << 15) | p;
+                    if (second) linfo1 = info; else linfo0 = info;
+                }
+            }
+            const uint32_t bal0 = __ballot_sync(0xffffffffu, th[0] != 0u);
+            const uint32_t bal1 = __ballot_sync(0xffffffffu, th[1] != 0u);
+            // device lines in front of a window's first top-level line
+            const uint32_t pre0 = kh[0] & ~th[0] & (th[0] ? (th[0] & (0u - th[0])) - 1u : 0xffffffffu);
+            const uint32_t pre1 = kh[1] & ~th[1] & (th[1] ? (th[1] & (0u - th[1])) - 1u : 0xffffffffu);
+            uint32_t last1;     // the chunk's last top-level line
+            uint32_t hw0, hw1;  // head lines: in front of the chunk's first top-level line
+            if (!__any_sync(0xffffffffu, any_alive)) {
+                // common case: nothing alive in this chunk.  Windows behind the chunk's first
+                // top-level line are dead, the ones in front of it are head lines.
+                const uint32_t bl = bal1 ? bal1 : bal0;
+                last1 = __shfl_sync(0xffffffffu, bal1 ? linfo1 : linfo0, bl ? 31 - __clz((int)bl) : 0);
+                if (bl == 0u) last1 = P_NONE;
+                hw0 = (bal0 & lt_mask) == 0u ? pre0 : 0u;
+                hw1 = (bal0 == 0u && (bal1 & lt_mask) == 0u) ? pre1 : 0u;
+            } else {
+                // governing line of every window inside the chunk (P_NONE: none, head lines)
+                const uint32_t s0 = bal0 & lt_mask, s1 = bal1 & lt_mask;
+                const uint32_t x0 = __shfl_sync(0xffffffffu, linfo0, s0 ? 31 - __clz((int)s0) : 0);
+                const uint32_t l0 = __shfl_sync(0xffffffffu, linfo0, bal0 ? 31 - __clz((int)bal0) : 0);
+                const uint32_t x1 = __shfl_sync(0xffffffffu, linfo1, s1 ? 31 - __clz((int)s1) : 0);
+                const uint32_t l1 = __shfl_sync(0xffffffffu, linfo1, bal1 ? 31 - __clz((int)bal1) : 0);
+                const uint32_t last0 = bal0 ? l0 : base_info;
+                const uint32_t cin0 = s0 ? x0 : base_info;
+                const uint32_t cin1 = s1 ? x1 : last0;
+                last1 = bal1 ? l1 : last0;
+                // governed by an alive line of an earlier window of this chunk: fold now
+                if (cin0 != P_NONE && (cin0 >> 31))
+                    fold_lines(P.tab, st, cbase, pre0, lane * 32u + 1u, ((cin0 >> 15) & 0xffffu) << 16, cbase + (cin0 & 0x7fffu));
+                if (cin1 != P_NONE && (cin1 >> 31))
+                    fold_lines(P.tab, st, cbase, pre1, (uint32_t)HALF + lane * 32u + 1u, ((cin1 >> 15) & 0xffffu) << 16, cbase + (cin1 & 0x7fffu));
+                hw0 = cin0 == P_NONE ? pre0 : 0u;
+                hw1 = cin1 == P_NONE ? pre1 : 0u;
+            }
+            // head lines: governed by the carry (not known yet: the resolve kernel looks at them)
+            if (rc_x & LS_VOK) {
+                uint32_t key_hi = ((rc_x >> 12) & 0xffffu) << 16;
+                unsigned long long anchor = P.base + (unsigned long long)rc_g * CW + (rc_x & 0xfffu);
+                if (rc_g == 0xffffffffu) {
+                    key_hi = ((uint32_t)(P.carry_in >> 44) & 0xffffu) << 16;
+                    anchor = P.carry_in & CV_ANCHOR_MASK;
+                }
+                // still the first line of its id?
+                if ((hw0 | hw1) != 0u && P.tab.vendor_first[key_hi >> 16] >= anchor) {
+                    fold_lines(P.tab, st, cbase, hw0, lane * 32u + 1u, key_hi, anchor);
+                    fold_lines(P.tab, st, cbase, hw1, (uint32_t)HALF + lane * 32u + 1u, key_hi, anchor);
+                }
+            }
+            if (last1 != P_NONE) {
+                if (rc_x == 0u) lead = i + 1u;  // chunks 0..i have head lines nobody judged
+                rc_x = LS_PUB | LS_TOP | ((last1 >> 31) ? LS_VOK : 0u) | (((last1 >> 15) & 0xffffu) << 12) | (last1 & 0xfffu);
+                rc_g = g;
+            }
+            // 2 KiB without a newline may belong to a >= 64 KiB line (bufio.ErrTooLong): raise the
+            // hint, the exact cut-off is then computed by trunc_kernel (never for real pci.ids)
+            if ((bal0 | bal1) == 0u && n_rel > (uint32_t)CW && __reduce_or_sync(0xffffffffu, rawnl | hw0 | hw1) == 0u && lane == 0)
+                atomicOr(&P.tab.counters[KX_C_LONGLINE_HINT], 1u);
+
+            // the stage is free: prefetch the chunk three steps ahead into it (this range or the next)
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t fi = i + (uint32_t)STAGES5;
+                if (fi < (uint32_t)RCH5) {
+                    if (gb + fi < P.num_chunks) issue(gb + fi, s);
+                } else if (r_next < P.num_ranges) {
+                    const uint32_t fg = r_next * RCH5 + (fi - (uint32_t)RCH5);
+                    if (fg < P.num_chunks) issue(fg, s);
+                }
+            }
+            s = s == (uint32_t)STAGES5 - 1u ? 0u : s + 1u;
+        }
+        // the range's inclusive carry and its unjudged leading chunks for the resolve kernel
+        if (lane == 0) {
+            unsigned long long v = ST_NONE;
+            if (rc_x != 0u) {
+                if (rc_g == 0xffffffffu)
+                    v = ST_PREFIX | P.carry_in;
+                else
+                    v = ST_PREFIX | CV_HAS_TOP | ((rc_x & LS_VOK) ? CV_VOK : 0ull) | ((unsigned long long)((rc_x >> 12) & 0xffffu) << 44) |
+                        ((P.base + (unsigned long long)rc_g * CW + (rc_x & 0xfffu)) & CV_ANCHOR_MASK);
+            }
+            P.range_state[r] = v;
+            P.lead[r] = lead < cnt ? lead : cnt;
+        }
+        r = r_next;
+        r_next = __shfl_sync(0xffffffffu, tk2, 0);
+        if (r >= P.num_ranges) break;
+    }
+}
+
+// Resolve, step 1: the leading chunks of every range, whose governing line was not known to the
+// warp that parsed them.  One thread per range walks back over the range status words (all
+// published now).  The governing line is dead for all but the first copy of a vendor block; only
+// then the range's leading chunks are queued for step 2.
+__global__ void __launch_bounds__(256) resolve_ranges_kernel(const Params5 P) {
+    const uint32_t rr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rr >= P.num_ranges) return;
+    const uint32_t nlead = P.lead[rr];
+    if (nlead == 0u) return;
+    // no top-level line between the start of the range and those chunks' head lines: the carry
+    // into the range governs them
+    unsigned long long carry = 0;
+    for (long long q = (long long)rr - 1;; q--) {
+        const unsigned long long sv = q >= 0 ? P.range_state[q] : (ST_PREFIX | P.carry_in);
+        if ((sv & ST_MASK) == ST_PREFIX) {
+            carry = sv & ~ST_MASK;
+            break;
+        }
+    }
+    const bool alive = (carry & CV_HAS_TOP) && (carry & CV_VOK) &&
+                       P.tab.vendor_first[(uint32_t)(carry >> 44) & 0xffffu] >= (carry & CV_ANCHOR_MASK);  // vendor_first is final here
+    if (!alive) return;
+    P.range_carry[rr] = carry;
+    const uint32_t at = atomicAdd(&P.tab.counters[KX_C_DEFER], nlead);
+    for (uint32_t j = 0; j < nlead; j++) P.tasks[at + j] = rr * RCH5 + j;
+}
+
+// Resolve, step 2: one warp per queued chunk stages it again and folds its head lines (the
+// device lines in front of its first top-level line) under the range's governing line.
+__global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Params5 P) {
+    __shared__ __align__(16) uint8_t stg[RES_WARPS][STG_BYTES];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t k7f = 0x7f7f7f7fu, k0a = 0x0a0a0a0au, k80 = 0x80808080u;
+    asm volatile("" : "+r"(k7f), "+r"(k0a), "+r"(k80));
+    const uint32_t st = smem_u32(stg[w]);
+    const uint32_t n_tasks = P.tab.counters[KX_C_DEFER];
+    for (uint32_t t = blockIdx.x * RES_WARPS + w; t < n_tasks; t += gridDim.x * RES_WARPS) {
+        const uint32_t gg = P.tasks[t];
+        const unsigned long long cc = P.range_carry[gg / RCH5];
+        const uint32_t key_hi = ((uint32_t)(cc >> 44) & 0xffffu) << 16;
+        const unsigned long long anchor = cc & CV_ANCHOR_MASK;
+        const uint32_t n_rel = stage_chunk_manual(P.text, P.n, gg, lane, stg[w]);
+        uint32_t kh[2], th[2], rawnl;
+        chunk_masks(st, lane, n_rel, k7f, k0a, k80, kh, th, rawnl);
+        const uint32_t bal0 = __ballot_sync(0xffffffffu, th[0] != 0u);
+        const uint32_t bal1 = __ballot_sync(0xffffffffu, th[1] != 0u);
+        const uint32_t pre0 = kh[0] & ~th[0] & (th[0] ? (th[0] & (0u - th[0])) - 1u : 0xffffffffu);
+        const uint32_t pre1 = kh[1] & ~th[1] & (th[1] ? (th[1] & (0u - th[1])) - 1u : 0xffffffffu);
+        const unsigned long long cbase = P.base + (unsigned long long)gg * CW;
+        if ((bal0 & lt_mask) == 0u) fold_lines(P.tab, st, cbase, pre0, lane * 32u + 1u, key_hi, anchor);
+        if (bal0 == 0u && (bal1 & lt_mask) == 0u) fold_lines(P.tab, st, cbase, pre1, (uint32_t)HALF + lane * 32u + 1u, key_hi, anchor);
+        __syncwarp();
+    }
+}
+
+}  // namespace kxparse5
