@@ -62,10 +62,58 @@ struct Params5 {
     unsigned long long carry_in;
 };
 
+
+// Newline masks of the chunk staged at shared address st (see kxparse4::chunk_masks for the
+// window layout): nl[h] bit b = a line starts after the newline at byte b of the lane's window in
+// KiB half h, trimmed to real line starts (< n_rel).
+__device__ __forceinline__ void nl_masks(uint32_t st, uint32_t lane, uint32_t n_rel, uint32_t k7f, uint32_t k0a, uint32_t k80,
+                                         uint32_t (&nl)[2], uint32_t &rawnl) {
+    const uint32_t swz = (lane >> 2) & 1u;
+    rawnl = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t o = (uint32_t)h * HALF + lane * 32u;
+        const uint4 va = kxparse4::lds128(st + o + 16u * swz);
+        const uint4 vb = kxparse4::lds128(st + o + 16u * (swz ^ 1u));
+        const uint32_t ma = nl_mask16(va, k7f, k0a, k80), mb = nl_mask16(vb, k7f, k0a, k80);
+        uint32_t mm = swz ? (mb | (ma << 16)) : (ma | (mb << 16));
+        rawnl |= mm;
+        if (n_rel <= (uint32_t)CW) mm &= n_rel > o + 1u ? (n_rel - o - 1u >= 32u ? 0xffffffffu : ((1u << (n_rel - o - 1u)) - 1u)) : 0u;
+        nl[h] = mm;
+    }
+}
+
+// top-level line starts among the line starts mm of one window (first byte neither '\t' nor
+// '#': device_plugin.go:229-236); lp = shared address of the byte after the window's byte 0
+__device__ __forceinline__ uint32_t tops_of(uint32_t lp, uint32_t mm) {
+    uint32_t tm = 0;
+    while (mm) {
+        const uint32_t bit = mm & (0u - mm);
+        mm ^= bit;
+        const uint32_t c0 = lds8(lp + (31u - (uint32_t)__clz((int)bit)));
+        if (c0 != 9u && c0 != 35u) tm |= bit;
+    }
+    return tm;
+}
+
+// device line candidates ("\t" + non-tab, :237) among the line starts mm of one window
+__device__ __forceinline__ uint32_t devs_of(uint32_t lp, uint32_t mm) {
+    uint32_t km = 0;
+    while (mm) {
+        const uint32_t bit = mm & (0u - mm);
+        mm ^= bit;
+        const uint32_t a = lp + (31u - (uint32_t)__clz((int)bit));
+        if (lds8(a) == 9u && lds8(a + 1u) != 9u) km |= bit;
+    }
+    return km;
+}
+
 __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     WarpSmem5 *W = reinterpret_cast<WarpSmem5 *>(smem_raw);
-    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t lane = threadIdx.x & 31u;
+    const uint32_t w = threadIdx.x >> 5;
+    asm volatile("" : "+r"(lane));  // opaque: no S2R SR_TID.X in the loop
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     if (lane == 0) {
@@ -82,8 +130,9 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
     if (r >= P.num_ranges) return;
 
     // shared-window addresses (see kxparse4::lds128)
-    const uint32_t a_stage0 = smem_u32(smem_raw) + w * (uint32_t)sizeof(WarpSmem5);  // stage s: + s * STG_BYTES
-    const uint32_t a_bar0 = a_stage0 + (uint32_t)offsetof(WarpSmem5, bar);           // bar s:   + 8 * s
+    uint32_t a_stage0 = smem_u32(smem_raw) + w * (uint32_t)sizeof(WarpSmem5);  // stage s: + s * STG_BYTES
+    asm volatile("" : "+r"(a_stage0));  // opaque: keep it in a register instead of re-deriving it (S2R + LEA + IMAD) at every use
+    const uint32_t a_bar0 = a_stage0 + (uint32_t)offsetof(WarpSmem5, bar);     // bar s:   + 8 * s
 
     uint32_t k7f = 0x7f7f7f7fu, k0a = 0x0a0a0a0au, k80 = 0x80808080u;
     asm volatile("" : "+r"(k7f), "+r"(k0a), "+r"(k80));
@@ -131,46 +180,24 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
                 n_rel = stage_chunk_manual(P.text, P.n, g, lane, W[w].stage[s]);
             }
 
-            uint32_t kh[2], th[2], rawnl;
-            chunk_masks(st, lane, n_rel, k7f, k0a, k80, kh, th, rawnl);
-
-            // the shard starts with a line start at p = 0 (no newline before it)
-            uint32_t base_info = P_NONE;  // top-level line in front of the lane windows (only that one)
-            if (g == 0u && n_rel > 0u) {
-                const uint32_t c0 = lds8(st), c1 = lds8(st + 1u);
-                if (c0 != (uint32_t)'#' && c0 != (uint32_t)'\t') {
-                    uint32_t val;
-                    const bool ok = hex4_swar(lds32_unaligned(st), val);
-                    bool alive = ok;
-                    if (ok) {
-                        const unsigned long long vf = P.tab.vendor_first[val];
-                        if (lane == 0 && cbase < vf) atomicMin(&P.tab.vendor_first[val], cbase);
-                        alive = cbase <= vf;
-                    }
-                    base_info = (alive ? 0x80000000u : 0u) | ((ok ? val : 0u) << 15);
-                } else if (c0 == (uint32_t)'\t' && c1 != (uint32_t)'\t') {
-                    // device line at the very start: governed by the shard's carry-in, which is known
-                    uint32_t dv;
-                    if (lane == 0 && (P.carry_in & CV_HAS_TOP) && (P.carry_in & CV_VOK) && hex4_swar(lds32_unaligned(st + 1u), dv))
-                        table_fold(P.tab, (((uint32_t)(P.carry_in >> 44) & 0xffffu) << 16) | dv, cbase, P.carry_in & CV_ANCHOR_MASK);
-                }
-            }
+            uint32_t nl[2], th[2], rawnl;
+            nl_masks(st, lane, n_rel, k7f, k0a, k80, nl, rawnl);
+            th[0] = tops_of(st + lane * 32u + 1u, nl[0]);
+            th[1] = tops_of(st + (uint32_t)HALF + lane * 32u + 1u, nl[1]);
 
             // top-level lines, by the lane that owns them: a candidate vendor anchor; only the FIRST
             // line with this prefix counts (:265).  If an earlier one is already known, this block
             // can never produce a hit (a hit needs min_anchor == vendor_first): it is dead.
             uint32_t linfo0 = P_NONE, linfo1 = P_NONE;  // last top-level line of my windows: alive<<31 | vendor<<15 | position
-            bool any_alive = base_info != P_NONE;
+            bool any_alive = (g == 0u) || (rc_x & LS_VOK) != 0u;  // the shard's first chunk and alive carries take the full path
             {
                 uint32_t t0 = th[0], t1 = th[1];
                 while (t0 | t1) {
                     const bool second = t0 == 0u;
                     const uint32_t tmv = second ? t1 : t0;
                     const uint32_t bit = tmv & (0u - tmv);
-                    const uint32_t rest = tmv ^ bit;
-                    if (second) t1 = rest; else t0 = rest;
-                    const uint32_t pbase = (second ? (uint32_t)HALF : 0u) + lane * 32u + 1u;
-                    const uint32_t p = pbase + (31u - (uint32_t)__clz((int)bit));
+                    if (second) t1 = tmv ^ bit; else t0 = tmv ^ bit;
+                    const uint32_t p = (second ? (uint32_t)HALF : 0u) + lane * 32u + 1u + (31u - (uint32_t)__clz((int)bit));
                     uint32_t val;
                     const bool ok = hex4_swar(lds32_unaligned(st + p), val);
                     const unsigned long long line_g = cbase + p;
@@ -180,34 +207,75 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
                         if (line_g < vf) atomicMin(&P.tab.vendor_first[val], line_g);
                         alive = line_g <= vf;
                     }
-                    if (alive) {
-                        // device lines of my window between this line and the next top-level line
-                        const uint32_t nxt = rest & (0u - rest);
-                        const uint32_t seg = (second ? kh[1] & ~th[1] : kh[0] & ~th[0]) & ~(bit | (bit - 1u)) & (nxt ? nxt - 1u : 0xffffffffu);
-                        fold_lines(P.tab, st, cbase, seg, pbase, val << 16, line_g);
-                        any_alive = true;
-                    }
+                    any_alive |= alive;
                     const uint32_t info = (alive ? 0x80000000u : 0u) | ((ok ? val : 0u) << 15) | p;
                     if (second) linfo1 = info; else linfo0 = info;
                 }
             }
             const uint32_t bal0 = __ballot_sync(0xffffffffu, th[0] != 0u);
             const uint32_t bal1 = __ballot_sync(0xffffffffu, th[1] != 0u);
-            // device lines in front of a window's first top-level line
-            const uint32_t pre0 = kh[0] & ~th[0] & (th[0] ? (th[0] & (0u - th[0])) - 1u : 0xffffffffu);
-            const uint32_t pre1 = kh[1] & ~th[1] & (th[1] ? (th[1] & (0u - th[1])) - 1u : 0xffffffffu);
-            uint32_t last1;     // the chunk's last top-level line
-            uint32_t hw0, hw1;  // head lines: in front of the chunk's first top-level line
+            uint32_t last1;  // the chunk's last top-level line
             if (!__any_sync(0xffffffffu, any_alive)) {
-                // common case: nothing alive in this chunk.  Windows behind the chunk's first
-                // top-level line are dead, the ones in front of it are head lines.
+                // common case: nothing alive in or in front of this chunk -- no device line of it
+                // can matter, none is looked at
                 const uint32_t bl = bal1 ? bal1 : bal0;
                 last1 = __shfl_sync(0xffffffffu, bal1 ? linfo1 : linfo0, bl ? 31 - __clz((int)bl) : 0);
                 if (bl == 0u) last1 = P_NONE;
-                hw0 = (bal0 & lt_mask) == 0u ? pre0 : 0u;
-                hw1 = (bal0 == 0u && (bal1 & lt_mask) == 0u) ? pre1 : 0u;
             } else {
-                // governing line of every window inside the chunk (P_NONE: none, head lines)
+                // full path: device line candidates, governing line of every window
+                uint32_t kh[2];
+                kh[0] = th[0] | devs_of(st + lane * 32u + 1u, nl[0] & ~th[0]);
+                kh[1] = th[1] | devs_of(st + (uint32_t)HALF + lane * 32u + 1u, nl[1] & ~th[1]);
+
+                // the shard starts with a line start at p = 0 (no newline before it)
+                uint32_t base_info = P_NONE;  // top-level line in front of the lane windows (only that one)
+                if (g == 0u && n_rel > 0u) {
+                    const uint32_t c0 = lds8(st), c1 = lds8(st + 1u);
+                    if (c0 != (uint32_t)'#' && c0 != (uint32_t)'\t') {
+                        uint32_t val;
+                        const bool ok = hex4_swar(lds32_unaligned(st), val);
+                        bool alive = ok;
+                        if (ok) {
+                            const unsigned long long vf = P.tab.vendor_first[val];
+                            if (lane == 0 && cbase < vf) atomicMin(&P.tab.vendor_first[val], cbase);
+                            alive = cbase <= vf;
+                        }
+                        base_info = (alive ? 0x80000000u : 0u) | ((ok ? val : 0u) << 15);
+                    } else if (c0 == (uint32_t)'\t' && c1 != (uint32_t)'\t') {
+                        // device line at the very start: governed by the shard's carry-in, which is known
+                        uint32_t dv;
+                        if (lane == 0 && (P.carry_in & CV_HAS_TOP) && (P.carry_in & CV_VOK) && hex4_swar(lds32_unaligned(st + 1u), dv))
+                            table_fold(P.tab, (((uint32_t)(P.carry_in >> 44) & 0xffffu) << 16) | dv, cbase, P.carry_in & CV_ANCHOR_MASK);
+                    }
+                }
+                // device lines behind the top-level lines of my windows (alive ones only)
+                linfo0 = linfo1 = P_NONE;
+                {
+                    uint32_t t0 = th[0], t1 = th[1];
+                    while (t0 | t1) {
+                        const bool second = t0 == 0u;
+                        const uint32_t tmv = second ? t1 : t0;
+                        const uint32_t bit = tmv & (0u - tmv);
+                        const uint32_t rest = tmv ^ bit;
+                        if (second) t1 = rest; else t0 = rest;
+                        const uint32_t pbase = (second ? (uint32_t)HALF : 0u) + lane * 32u + 1u;
+                        const uint32_t p = pbase + (31u - (uint32_t)__clz((int)bit));
+                        uint32_t val;
+                        const bool ok = hex4_swar(lds32_unaligned(st + p), val);
+                        const unsigned long long line_g = cbase + p;
+                        const bool alive = ok && line_g <= P.tab.vendor_first[val];  // updated by the loop above
+                        if (alive) {
+                            const uint32_t nxt = rest & (0u - rest);
+                            const uint32_t seg = (second ? kh[1] & ~th[1] : kh[0] & ~th[0]) & ~(bit | (bit - 1u)) & (nxt ? nxt - 1u : 0xffffffffu);
+                            fold_lines(P.tab, st, cbase, seg, pbase, val << 16, line_g);
+                        }
+                        const uint32_t info = (alive ? 0x80000000u : 0u) | ((ok ? val : 0u) << 15) | p;
+                        if (second) linfo1 = info; else linfo0 = info;
+                    }
+                }
+                // device lines in front of a window's first top-level line
+                const uint32_t pre0 = kh[0] & ~th[0] & (th[0] ? (th[0] & (0u - th[0])) - 1u : 0xffffffffu);
+                const uint32_t pre1 = kh[1] & ~th[1] & (th[1] ? (th[1] & (0u - th[1])) - 1u : 0xffffffffu);
                 const uint32_t s0 = bal0 & lt_mask, s1 = bal1 & lt_mask;
                 const uint32_t x0 = __shfl_sync(0xffffffffu, linfo0, s0 ? 31 - __clz((int)s0) : 0);
                 const uint32_t l0 = __shfl_sync(0xffffffffu, linfo0, bal0 ? 31 - __clz((int)bal0) : 0);
@@ -217,26 +285,27 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
                 const uint32_t cin0 = s0 ? x0 : base_info;
                 const uint32_t cin1 = s1 ? x1 : last0;
                 last1 = bal1 ? l1 : last0;
-                // governed by an alive line of an earlier window of this chunk: fold now
+                // governed by an alive line of an earlier window of this chunk
                 if (cin0 != P_NONE && (cin0 >> 31))
                     fold_lines(P.tab, st, cbase, pre0, lane * 32u + 1u, ((cin0 >> 15) & 0xffffu) << 16, cbase + (cin0 & 0x7fffu));
                 if (cin1 != P_NONE && (cin1 >> 31))
                     fold_lines(P.tab, st, cbase, pre1, (uint32_t)HALF + lane * 32u + 1u, ((cin1 >> 15) & 0xffffu) << 16, cbase + (cin1 & 0x7fffu));
-                hw0 = cin0 == P_NONE ? pre0 : 0u;
-                hw1 = cin1 == P_NONE ? pre1 : 0u;
-            }
-            // head lines: governed by the carry (not known yet: the resolve kernel looks at them)
-            if (rc_x & LS_VOK) {
-                uint32_t key_hi = ((rc_x >> 12) & 0xffffu) << 16;
-                unsigned long long anchor = P.base + (unsigned long long)rc_g * CW + (rc_x & 0xfffu);
-                if (rc_g == 0xffffffffu) {
-                    key_hi = ((uint32_t)(P.carry_in >> 44) & 0xffffu) << 16;
-                    anchor = P.carry_in & CV_ANCHOR_MASK;
-                }
-                // still the first line of its id?
-                if ((hw0 | hw1) != 0u && P.tab.vendor_first[key_hi >> 16] >= anchor) {
-                    fold_lines(P.tab, st, cbase, hw0, lane * 32u + 1u, key_hi, anchor);
-                    fold_lines(P.tab, st, cbase, hw1, (uint32_t)HALF + lane * 32u + 1u, key_hi, anchor);
+                // head lines (in front of the chunk's first top-level line): governed by the carry; if
+                // that is not known yet, the resolve kernels look at them
+                const uint32_t hw0 = cin0 == P_NONE ? pre0 : 0u;
+                const uint32_t hw1 = cin1 == P_NONE ? pre1 : 0u;
+                if (rc_x & LS_VOK) {
+                    uint32_t key_hi = ((rc_x >> 12) & 0xffffu) << 16;
+                    unsigned long long anchor = P.base + (unsigned long long)rc_g * CW + (rc_x & 0xfffu);
+                    if (rc_g == 0xffffffffu) {
+                        key_hi = ((uint32_t)(P.carry_in >> 44) & 0xffffu) << 16;
+                        anchor = P.carry_in & CV_ANCHOR_MASK;
+                    }
+                    // still the first line of its id?
+                    if ((hw0 | hw1) != 0u && P.tab.vendor_first[key_hi >> 16] >= anchor) {
+                        fold_lines(P.tab, st, cbase, hw0, lane * 32u + 1u, key_hi, anchor);
+                        fold_lines(P.tab, st, cbase, hw1, (uint32_t)HALF + lane * 32u + 1u, key_hi, anchor);
+                    }
                 }
             }
             if (last1 != P_NONE) {
@@ -246,7 +315,7 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
             }
             // 2 KiB without a newline may belong to a >= 64 KiB line (bufio.ErrTooLong): raise the
             // hint, the exact cut-off is then computed by trunc_kernel (never for real pci.ids)
-            if ((bal0 | bal1) == 0u && n_rel > (uint32_t)CW && __reduce_or_sync(0xffffffffu, rawnl | hw0 | hw1) == 0u && lane == 0)
+            if ((bal0 | bal1) == 0u && n_rel > (uint32_t)CW && __reduce_or_sync(0xffffffffu, rawnl) == 0u && lane == 0)
                 atomicOr(&P.tab.counters[KX_C_LONGLINE_HINT], 1u);
 
             // the stage is free: prefetch the chunk three steps ahead into it (this range or the next)
