@@ -246,7 +246,7 @@ def main():
         step().free()
     for _ in range(args.settle_steps):  # ~0.5 s of untimed steps: clocks settle and nvidia-smi gets samples (same count on all ranks)
         step().free()
-    parse_ms, fin_ms, merge_ms, look_ms = [], [], [], []
+    parse_ms, fin_ms, merge_ms, look_ms, res_ms = [], [], [], [], []
     barrier()
     launches0 = kx.launch_count()
     kx.timer_begin()
@@ -267,6 +267,7 @@ def main():
         t = load()
         tm = kx.timings()
         parse_ms.append(tm[K.binding.T_PARSE]); fin_ms.append(tm[K.binding.T_FINALIZE]); merge_ms.append(tm[K.binding.T_MERGE])
+        res_ms.append(tm[K.binding.T_RESOLVE])
         kx.lookup_device(t, d_keys, NQ, d_rows)
         look_ms.append(kx.timings()[K.binding.T_LOOKUP])
         t.free()
@@ -328,11 +329,11 @@ def main():
                        "l2": "input (1.458 GB) larger than L2 (126 MB); no flush needed"},
             "lookups_per_s": world * NQ / (float(np.mean(look_ms)) * 1e-3),
             "lookups_per_s_e2e": world * NQ / (float(np.mean(lk_ms)) * 1e-3),
-            "kernel_ms": {"parse": pk, "finalize": float(np.mean(fin_ms)), "merge": float(np.mean(merge_ms)),
+            "kernel_ms": {"parse": pk, "parse_resolve": float(np.mean(res_ms)), "finalize": float(np.mean(fin_ms)), "merge": float(np.mean(merge_ms)),
                           "lookup": float(np.mean(look_ms))},
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "kxparse3::parse_kernel_v3",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "kxparse5::parse_kernel_v5",
                          "algorithmic_bytes_per_launch": n},
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(n + 4 * NQ),
                     "d2h_bytes_per_step": int(4 * NQ), "ms_per_step": e2e_step},

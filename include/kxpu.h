@@ -69,6 +69,7 @@ uint64_t kxpu_launch_count(kxpu_ctx *ctx);
 #define KXPU_T_CLASSIFY 4
 #define KXPU_T_EMIT     5
 #define KXPU_T_MERGE    6
+#define KXPU_T_RESOLVE  7  /* parse: second pass over the chunks whose governing line was not known */
 #define KXPU_T_COUNT    8
 int32_t kxpu_last_timings(kxpu_ctx *ctx, float ms_out[KXPU_T_COUNT]);
 /* Device-side stopwatch over an arbitrary sequence of calls on this ctx: begin records a

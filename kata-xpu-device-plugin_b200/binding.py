@@ -15,7 +15,7 @@ E_INVALID, E_CUDA, E_NOGPU, E_NOSPACE, E_CAPACITY, E_NCCL, E_UNSUPPORTED, E_NOME
 ROW_MISS = -1
 REJECTED = 0xFFFFFFFF
 FMT_YAML, FMT_JSON = 0, 1
-T_PARSE, T_FINALIZE, T_LOOKUP, T_NAMES, T_CLASSIFY, T_EMIT, T_MERGE, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
+T_PARSE, T_FINALIZE, T_LOOKUP, T_NAMES, T_CLASSIFY, T_EMIT, T_MERGE, T_RESOLVE, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
 COMM_ID_BYTES = 128
 
 REC_VENDOR_ERR, REC_DRIVER_ERR, REC_IOMMU_ERR, REC_DEVICE_ERR, REC_IS_DIR = 1, 2, 4, 8, 16

@@ -202,7 +202,8 @@ static void table_release(kxpu_ctx *ctx, kxpu_table *t) {
     delete t;
 }
 
-static int32_t table_alloc(kxpu_ctx *ctx, uint32_t cap, uint32_t blob_cap, uint32_t num_tiles, kxpu_table **out) {
+static int32_t table_alloc(kxpu_ctx *ctx, uint32_t cap, uint32_t blob_cap, uint32_t num_tiles, kxpu_table **out,
+                           bool zero_tiles = true) {
     kxpu_table *t = new (std::nothrow) kxpu_table();
     if (!t) return KXPU_E_NOMEM;
     t->cap = cap;
@@ -257,7 +258,8 @@ static int32_t table_alloc(kxpu_ctx *ctx, uint32_t cap, uint32_t blob_cap, uint3
     t->blob = b + o_blob;
     t->blob_cap = blob_cap;
     cudaMemsetAsync(b, 0xff, ff_bytes, ctx->stream);
-    cudaMemsetAsync(b + ff_bytes, 0, zero_bytes, ctx->stream);
+    // the v5 parse kernels write every status word they read: only the counters need zeroing
+    cudaMemsetAsync(b + ff_bytes, 0, zero_tiles ? zero_bytes : o_tiles - ff_bytes, ctx->stream);
     *out = t;
     return KXPU_OK;
 }
@@ -333,7 +335,7 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
         const uint32_t tile_bytes = version == 1 ? (uint32_t)kxparse::T : (uint32_t)kxparse2::CW;
         const uint32_t num_tiles = (uint32_t)((n + tile_bytes - 1) / tile_bytes);
         const uint32_t num_sc = (num_tiles + kxparse3::SCC - 1) / kxparse3::SCC;
-        int32_t rc = table_alloc(ctx, cap, blob_cap, num_tiles, &t);
+        int32_t rc = table_alloc(ctx, cap, blob_cap, num_tiles, &t, version != 5);
         if (rc != KXPU_OK) return rc;
         if (num_tiles > 0) {
             KxTimer tm(ctx, KXPU_T_PARSE);
@@ -357,6 +359,8 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
                 if (grid > need) grid = need;
                 kxparse5::parse_kernel_v5<<<grid, kxparse2::NT, smem, ctx->stream>>>(P);
                 KX_LAUNCHED(ctx);
+                tm.stop();
+                KxTimer tr(ctx, KXPU_T_RESOLVE);
                 kxparse5::resolve_ranges_kernel<<<(P.num_ranges + 255u) / 256u, 256, 0, ctx->stream>>>(P);
                 KX_LAUNCHED(ctx);
                 kxparse5::resolve_chunks_kernel<<<4 * ctx->sm_count, kxparse5::RES_WARPS * 32, 0, ctx->stream>>>(P);

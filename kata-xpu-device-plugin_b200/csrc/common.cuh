@@ -43,8 +43,12 @@ struct kxpu_ctx {
 struct KxTimer {  // records a CUDA-event pair around a stage on the ctx stream
     kxpu_ctx *c;
     int idx;
+    bool open = true;
     KxTimer(kxpu_ctx *ctx, int i) : c(ctx), idx(i) { cudaEventRecord(c->ev[2 * i], c->stream); }
-    ~KxTimer() { cudaEventRecord(c->ev[2 * idx + 1], c->stream); c->ev_used[idx] = true; }
+    void stop() {
+        if (open) { cudaEventRecord(c->ev[2 * idx + 1], c->stream); c->ev_used[idx] = true; open = false; }
+    }
+    ~KxTimer() { stop(); }
 };
 
 static inline void kx_clear_timings(kxpu_ctx *c) { memset(c->ev_used, 0, sizeof(c->ev_used)); }

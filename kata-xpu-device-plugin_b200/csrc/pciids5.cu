@@ -381,18 +381,38 @@ __global__ void __launch_bounds__(256) resolve_ranges_kernel(const Params5 P) {
 // device lines in front of its first top-level line) under the range's governing line.
 __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Params5 P) {
     __shared__ __align__(16) uint8_t stg[RES_WARPS][STG_BYTES];
+    __shared__ __align__(8) unsigned long long bars[RES_WARPS];
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t k7f = 0x7f7f7f7fu, k0a = 0x0a0a0a0au, k80 = 0x80808080u;
     asm volatile("" : "+r"(k7f), "+r"(k0a), "+r"(k80));
-    const uint32_t st = smem_u32(stg[w]);
+    const uint32_t st = smem_u32(stg[w]), bar = smem_u32(&bars[w]);
+    if (lane == 0) {
+        mbar_init(&bars[w], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const unsigned long long pol = l2_evict_first_policy();
     const uint32_t n_tasks = P.tab.counters[KX_C_DEFER];
+    uint32_t par = 0;
     for (uint32_t t = blockIdx.x * RES_WARPS + w; t < n_tasks; t += gridDim.x * RES_WARPS) {
         const uint32_t gg = P.tasks[t];
+        uint32_t n_rel = CW + 1;
+        if (gg < P.tma_limit) {
+            // one bulk copy instead of five dependent 16-byte round trips per lane
+            if (lane == 0) {
+                mbar_expect_tx_a(bar, STG_BYTES);
+                tma_load_a(st, P.text + (unsigned long long)gg * CW, STG_BYTES, bar, pol);
+            }
+            while (!mbar_try_a(bar, par)) {
+            }
+            par ^= 1u;
+        } else {
+            n_rel = stage_chunk_manual(P.text, P.n, gg, lane, stg[w]);
+        }
         const unsigned long long cc = P.range_carry[gg / RCH5];
         const uint32_t key_hi = ((uint32_t)(cc >> 44) & 0xffffu) << 16;
         const unsigned long long anchor = cc & CV_ANCHOR_MASK;
-        const uint32_t n_rel = stage_chunk_manual(P.text, P.n, gg, lane, stg[w]);
         uint32_t kh[2], th[2], rawnl;
         chunk_masks(st, lane, n_rel, k7f, k0a, k80, kh, th, rawnl);
         const uint32_t bal0 = __ballot_sync(0xffffffffu, th[0] != 0u);

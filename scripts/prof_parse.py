@@ -17,5 +17,5 @@ kx.replicate(d_big, d_one, n, copies)
 for it in range(iters):
     tb = kx.pciids_load_device(d_big, n * copies)
     tm = kx.timings()
-    print("iter %d rows %d parse %.3f ms %.1f GB/s finalize %.3f ms" % (it, tb.rows, tm[0], n * copies / tm[0] / 1e6, tm[1]))
+    print("iter %d rows %d parse %.3f ms %.1f GB/s resolve %.3f ms finalize %.3f ms" % (it, tb.rows, tm[0], n * copies / tm[0] / 1e6, tm[7], tm[1]))
     tb.free()
