@@ -434,7 +434,7 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
             version = 2;
             continue;
         }
-        if (ctx->h_ctl[KX_C_OVERFLOW]) {
+        if (ctx->h_ctl[KX_C_OVERFLOW] || ctx->h_ctl[KX_C_NKEYS] > t->dev.max_keys) {
             table_release(ctx, t);
             if (cap >= (1u << 28)) return KXPU_E_CAPACITY;
             cap <<= 2;
@@ -570,7 +570,7 @@ int32_t kx_table_from_gather(kxpu_ctx *ctx, void *d_gather, int R, size_t stride
             cudaFreeAsync(d_gather, ctx->stream);
             return KXPU_E_CUDA;
         }
-        if (ctx->h_ctl[KX_C_OVERFLOW]) {
+        if (ctx->h_ctl[KX_C_OVERFLOW] || ctx->h_ctl[KX_C_NKEYS] > t->dev.max_keys) {
             table_release(ctx, t);
             if (cap >= (1u << 28)) { cudaFreeAsync(d_gather, ctx->stream); return KXPU_E_CAPACITY; }
             cap <<= 2;

@@ -169,12 +169,14 @@ __device__ __forceinline__ void table_fold(const KxTableDev &tb, uint32_t key, u
     unsigned long long ml = tb.min_line[slot];
     if (key != KX_EMPTY_KEY && k != key) {
         uint32_t step = 0;
+        bool fresh = false;
         for (;;) {
             if (k == KX_EMPTY_KEY) {
                 uint32_t old = atomicCAS(&tb.keys[slot], KX_EMPTY_KEY, key);
                 if (old == KX_EMPTY_KEY) {
-                    uint32_t nk = atomicAdd(&tb.counters[KX_C_NKEYS], 1u) + 1u;
-                    if (nk > tb.max_keys) tb.counters[KX_C_OVERFLOW] = 1u;
+                    // the count is only compared with max_keys by the host (growth): fire and forget
+                    atomicAdd(&tb.counters[KX_C_NKEYS], 1u);
+                    fresh = true;
                     break;
                 }
                 if (old == key) break;
@@ -184,7 +186,8 @@ __device__ __forceinline__ void table_fold(const KxTableDev &tb, uint32_t key, u
             k = tb.keys[slot];
             if (k == key) break;
         }
-        ml = tb.min_line[slot];
+        // a slot this thread just claimed still holds the initial (maximal) minima: no need to read them
+        ml = fresh ? KX_NO_OFF : tb.min_line[slot];
     }
     if (line_g < ml) {
         atomicMin(&tb.min_line[slot], line_g);

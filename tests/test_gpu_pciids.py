@@ -237,3 +237,67 @@ def test_repeated_loads_are_deterministic(kx, pci_text, oracle_rows):
         tab.free()
     kx.dev_free(d_big)
     kx.dev_free(d_one)
+
+
+def _big_random_text(rng, n_lines, vendors, dup_prob):
+    """pci.ids-shaped text with blocks long enough to cross many 2 KiB chunks / 16 KiB ranges and
+    vendor ids that repeat (only the first block of an id may produce hits)."""
+    lines, seen = [], []
+    while len(lines) < n_lines:
+        v = int(rng.choice(seen)) if seen and rng.random() < dup_prob else int(rng.integers(0, vendors))
+        seen.append(v)
+        lines.append(b"%04x  Vendor %d\n" % (v, v))
+        for _ in range(int(rng.integers(0, 1500)) if rng.random() < 0.3 else int(rng.integers(0, 12))):
+            d = int(rng.integers(0, 0x10000))
+            lines.append(b"\t%04x  Device %d of %d\n" % (d, d, v))
+            if rng.random() < 0.3:
+                lines.append(b"\t\t%04x %04x  Subsystem\n" % (v, d))
+            if rng.random() < 0.02:
+                lines.append(b"# comment\n")
+    return b"".join(lines)
+
+
+def test_big_random_texts_many_ranges(kx, oracle):
+    """Texts of 0.3-2 MB: carries across chunks and ranges, alive and dead blocks interleaved,
+    blocks starting right before / after range boundaries."""
+    rng = np.random.default_rng(77)
+    for trial, (n_lines, vendors, dup) in enumerate([(12000, 300, 0.3), (40000, 50, 0.6), (60000, 4000, 0.05)]):
+        text = _big_random_text(rng, n_lines, vendors, dup)
+        if trial == 1:
+            text = b"\t0001  orphan before any vendor line\n" + text
+        keys = [int(rng.integers(0, vendors)) << 16 | int(rng.integers(0, 0x10000)) for _ in range(64)]
+        check_text(kx, oracle, text, extra_keys=keys)
+
+
+def test_block_boundaries_at_range_edges(kx, oracle):
+    """A vendor line placed exactly at / around every 2 KiB chunk and 16 KiB range boundary, the
+    block before it alive, the block after it a repeat of an earlier id (dead)."""
+    for edge in (2048, 16384, 16384 * 3, 16384 * 8):
+        for delta in (-9, -1, 0, 1, 2):
+            pad_lines = []
+            size = len(b"1111  first\n")
+            d = 0
+            while size + 14 < edge + delta:
+                pad_lines.append(b"\t%04x  pad %03d\n" % (d & 0xffff, d % 1000))
+                size += 14
+                d += 1
+            filler = b"#" + b"x" * max(0, edge + delta - size - 2) + b"\n" if edge + delta - size >= 2 else b""
+            text = (b"1111  first\n" + b"".join(pad_lines) + filler + b"2222  second\n\t0001  two-one\n" +
+                    b"1111  again\n\t0fff  hidden\n" + b"\t%04x  tail\n" % 7 * 900 + b"3333  third\n\t0003  t\n")
+            check_text(kx, oracle, text, extra_keys=[0x11110000, 0x11110fff, 0x22220001, 0x33330003, 0x11110007])
+
+
+@pytest.mark.parametrize("version", [1, 2, 3, 4, 5])
+def test_every_parse_kernel_generation_agrees(version, oracle, pci_text, monkeypatch):
+    """KXPU_PARSE_V selects the kernel generation when a context is created; all of them must
+    build the same table as the oracle."""
+    import kxpu_b200 as K
+    monkeypatch.setenv("KXPU_PARSE_V", str(version))
+    k = K.Kxpu(0)
+    try:
+        rng = np.random.default_rng(5)
+        check_text(k, oracle, pci_text[:300001])
+        check_text(k, oracle, pci_text[:pci_text.rfind(b"\n", 0, 150000) + 1] * 4)
+        check_text(k, oracle, _big_random_text(rng, 8000, 100, 0.4), extra_keys=[0x00010001, 0x00630000])
+    finally:
+        k.close()
