@@ -469,6 +469,7 @@ __global__ void __launch_bounds__(256) merge_insert_kernel(const uint8_t *gather
     const uint8_t *slab = gather + (size_t)r * stride;
     const SlabHeader *h = reinterpret_cast<const SlabHeader *>(slab);
     if (i == 0 && h->trunc != KX_NO_OFF) atomicMin(tab.trunc, h->trunc);
+    if (i == 0 && h->overflow) tab.counters[KX_C_SLAB_OVERFLOW] = 1u;  // some rank outgrew the slab: the host retries with larger ones
     if (i < h->n_rows) {
         const SlabRow row = reinterpret_cast<const SlabRow *>(slab + slab_rows_off())[i];
         kxparse2::table_fold(tab, row.key, row.line, row.anchor);
@@ -531,22 +532,9 @@ __global__ void __launch_bounds__(256) merge_names_kernel(const uint8_t *gather,
 
 int32_t kx_table_from_gather(kxpu_ctx *ctx, void *d_gather, int R, size_t stride, kxcomm::SlabCaps caps, kxpu_table **out) {
     using namespace kxcomm;
-    // headers first: a capacity overflow on any rank makes every rank retry with larger slabs
-    std::vector<SlabHeader> hdr((size_t)R);
-    for (int r = 0; r < R; r++)
-        cudaMemcpyAsync(&hdr[(size_t)r], (const uint8_t *)d_gather + (size_t)r * stride, sizeof(SlabHeader), cudaMemcpyDeviceToHost,
-                        ctx->stream);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-        KX_SET_ERR(ctx, "all-gather failed: %s", cudaGetErrorString(e));
-        cudaFreeAsync(d_gather, ctx->stream);
-        return KXPU_E_CUDA;
-    }
-    size_t total_rows = 0;
-    for (int r = 0; r < R; r++) {
-        if (hdr[(size_t)r].overflow) { cudaFreeAsync(d_gather, ctx->stream); return KXPU_E_CAPACITY; }
-        total_rows += hdr[(size_t)r].n_rows;
-    }
+    // No host round trip for the slab headers: the insert kernel flags a slab overflow of any rank
+    // in the counters that are read back anyway (every rank sees the same headers and retries alike).
+    cudaError_t e = cudaSuccess;
     if ((size_t)R * stride >= 0xFFFFFFFFull) { cudaFreeAsync(d_gather, ctx->stream); return KXPU_E_UNSUPPORTED; }
     uint32_t cap = 1u << 16;
     for (int attempt = 0; attempt < 8; attempt++) {
@@ -570,9 +558,14 @@ int32_t kx_table_from_gather(kxpu_ctx *ctx, void *d_gather, int R, size_t stride
             cudaFreeAsync(d_gather, ctx->stream);
             return KXPU_E_CUDA;
         }
+        if (ctx->h_ctl[KX_C_SLAB_OVERFLOW]) {
+            table_release(ctx, t);
+            cudaFreeAsync(d_gather, ctx->stream);
+            return KXPU_E_CAPACITY;
+        }
         if (ctx->h_ctl[KX_C_OVERFLOW] || ctx->h_ctl[KX_C_NKEYS] > t->dev.max_keys) {
             table_release(ctx, t);
-            if (cap >= (1u << 28)) { cudaFreeAsync(d_gather, ctx->stream); return KXPU_E_CAPACITY; }
+            if (cap >= (1u << 28)) { cudaFreeAsync(d_gather, ctx->stream); return KXPU_E_UNSUPPORTED; }
             cap <<= 2;
             continue;
         }

@@ -30,6 +30,7 @@
 #define KX_C_PEND_OVERFLOW 8
 #define KX_C_NSEL 9
 #define KX_C_DEFER 10
+#define KX_C_SLAB_OVERFLOW 11
 #define KX_C_COUNT 16
 
 struct KxTableDev {

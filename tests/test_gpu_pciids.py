@@ -301,3 +301,19 @@ def test_every_parse_kernel_generation_agrees(version, oracle, pci_text, monkeyp
         check_text(k, oracle, _big_random_text(rng, 8000, 100, 0.4), extra_keys=[0x00010001, 0x00630000])
     finally:
         k.close()
+
+
+def test_structural_byte_fuzz(kx, oracle):
+    """Random byte soup weighted towards the bytes the parser branches on (newline, tab, '#', hex
+    digits, CR, VT, NUL, high bytes): every window / chunk / range code path sees odd neighbours."""
+    rng = np.random.default_rng(99)
+    alphabet = np.frombuffer(b"\n\n\n\n\t\t\t##0123456789abcdefABCDEF  \r\x0b\x00\xff\x80xyz", dtype=np.uint8)
+    for trial in range(60):
+        n = int(rng.integers(1, 40000))
+        body = alphabet[rng.integers(0, len(alphabet), n)].tobytes()
+        if trial % 2 == 0:
+            # sprinkle well-formed vendor / device lines so that hits exist
+            pieces = [body[i:i + 257] for i in range(0, len(body), 257)]
+            body = b"".join(p + b"\n%04x  V\n\t%04x  D\n" % (int(rng.integers(0, 6)), int(rng.integers(0, 6))) for p in pieces)
+        keys = [(int(rng.integers(0, 6)) << 16) | int(rng.integers(0, 6)) for _ in range(16)]
+        check_text(kx, oracle, body, extra_keys=keys)
