@@ -96,6 +96,21 @@ __device__ __forceinline__ uint32_t tops_of(uint32_t lp, uint32_t mm) {
     return tm;
 }
 
+// the same for the lane's two windows (KiB halves) at once: one loop, both loads in flight
+__device__ __forceinline__ void tops_of2(uint32_t lp0, uint32_t m0, uint32_t m1, uint32_t &t0, uint32_t &t1) {
+    t0 = t1 = 0;
+    while (m0 | m1) {
+        const uint32_t b0 = m0 & (0u - m0), b1 = m1 & (0u - m1);
+        m0 ^= b0;
+        m1 ^= b1;
+        // an exhausted mask reads the byte in front of the window (31 - clz(0) = -1) and ORs in nothing
+        const uint32_t c0 = lds8(lp0 + (31u - (uint32_t)__clz((int)b0)));
+        const uint32_t c1 = lds8(lp0 + (uint32_t)HALF + (31u - (uint32_t)__clz((int)b1)));
+        if (c0 != 9u && c0 != 35u) t0 |= b0;
+        if (c1 != 9u && c1 != 35u) t1 |= b1;
+    }
+}
+
 // device line candidates ("\t" + non-tab, :237) among the line starts mm of one window
 __device__ __forceinline__ uint32_t devs_of(uint32_t lp, uint32_t mm) {
     uint32_t km = 0;
@@ -182,8 +197,7 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
 
             uint32_t nl[2], th[2], rawnl;
             nl_masks(st, lane, n_rel, k7f, k0a, k80, nl, rawnl);
-            th[0] = tops_of(st + lane * 32u + 1u, nl[0]);
-            th[1] = tops_of(st + (uint32_t)HALF + lane * 32u + 1u, nl[1]);
+            tops_of2(st + lane * 32u + 1u, nl[0], nl[1], th[0], th[1]);
 
             // top-level lines, by the lane that owns them: a candidate vendor anchor; only the FIRST
             // line with this prefix counts (:265).  If an earlier one is already known, this block
