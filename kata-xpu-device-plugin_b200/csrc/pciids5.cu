@@ -76,7 +76,8 @@ __device__ __forceinline__ void nl_masks(uint32_t st, uint32_t lane, uint32_t n_
         const uint4 va = kxparse4::lds128(st + o + 16u * swz);
         const uint4 vb = kxparse4::lds128(st + o + 16u * (swz ^ 1u));
         const uint32_t ma = nl_mask16(va, k7f, k0a, k80), mb = nl_mask16(vb, k7f, k0a, k80);
-        uint32_t mm = swz ? (mb | (ma << 16)) : (ma | (mb << 16));
+        const uint32_t m2 = ma | (mb << 16);
+        uint32_t mm = __funnelshift_l(m2, m2, swz << 4);  // swapped read order: swap the halves back
         rawnl |= mm;
         if (n_rel <= (uint32_t)CW) mm &= n_rel > o + 1u ? (n_rel - o - 1u >= 32u ? 0xffffffffu : ((1u << (n_rel - o - 1u)) - 1u)) : 0u;
         nl[h] = mm;
@@ -336,12 +337,8 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
             __syncwarp();
             if (lane == 0) {
                 const uint32_t fi = i + (uint32_t)STAGES5;
-                if (fi < (uint32_t)RCH5) {
-                    if (gb + fi < P.num_chunks) issue(gb + fi, s);
-                } else if (r_next < P.num_ranges) {
-                    const uint32_t fg = r_next * RCH5 + (fi - (uint32_t)RCH5);
-                    if (fg < P.num_chunks) issue(fg, s);
-                }
+                const uint32_t fg = fi < (uint32_t)RCH5 ? g + (uint32_t)STAGES5 : (r_next < P.num_ranges ? r_next * RCH5 + (fi - (uint32_t)RCH5) : 0xffffffffu);
+                issue(fg, s);
             }
             s = s == (uint32_t)STAGES5 - 1u ? 0u : s + 1u;
         }
