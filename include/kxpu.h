@@ -72,6 +72,9 @@ uint64_t kxpu_launch_count(kxpu_ctx *ctx);
 #define KXPU_T_RESOLVE  7  /* parse: second pass over the chunks whose governing line was not known */
 #define KXPU_T_COUNT    8
 int32_t kxpu_last_timings(kxpu_ctx *ctx, float ms_out[KXPU_T_COUNT]);
+/* The per-stage events cost a few microseconds per call; on = 0 drops them (kxpu_last_timings
+ * then reports nothing), on = 1 (default) restores them. */
+int32_t kxpu_set_stage_timing(kxpu_ctx *ctx, int32_t on);
 /* Device-side stopwatch over an arbitrary sequence of calls on this ctx: begin records a
  * CUDA event on the ctx stream, end records a second one, waits for it and returns the
  * elapsed milliseconds (bench.py times its K steps with this pair). */
@@ -126,6 +129,12 @@ int32_t kxpu_lookup(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *keys, size_t n
                     int32_t *rows_out);
 int32_t kxpu_lookup_device(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *d_keys, size_t n,
                            int32_t *d_rows_out);
+/* Parse and join in one call: what createDevicePlugins does for all device ids at start-up
+ * (getDeviceName per id, device_plugin.go:99 -> :208-259).  Same results as
+ * kxpu_pciids_load_device followed by kxpu_lookup_device; the join is enqueued behind the
+ * parse without a host round trip in between.  Text, keys and rows are device pointers. */
+int32_t kxpu_pciids_join_device(kxpu_ctx *ctx, const void *d_text, size_t n, const uint32_t *d_keys,
+                                size_t nq, int32_t *d_rows_out, kxpu_table **out);
 
 /* Sanitised resource names for row handles (device_plugin.go:241-251: TrimPrefix,
  * TrimSpace, ToUpper, '/'->'_', '.'->'_', \s+ -> '_', strip [^a-zA-Z0-9_.]).

@@ -30,10 +30,10 @@ assert DEVREC_DTYPE.itemsize == 64 and CDIDEV_DTYPE.itemsize == 32
 # every symbol include/kxpu.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "kxpu_ctx_create", "kxpu_ctx_destroy", "kxpu_strerror", "kxpu_last_error", "kxpu_launch_count",
-    "kxpu_last_timings", "kxpu_timer_begin", "kxpu_timer_end", "kxpu_dev_alloc", "kxpu_dev_free", "kxpu_dev_upload", "kxpu_dev_download",
+    "kxpu_last_timings", "kxpu_set_stage_timing", "kxpu_timer_begin", "kxpu_timer_end", "kxpu_dev_alloc", "kxpu_dev_free", "kxpu_dev_upload", "kxpu_dev_download",
     "kxpu_dev_replicate", "kxpu_pinned_alloc", "kxpu_pinned_free", "kxpu_sync", "kxpu_pciids_load",
     "kxpu_pciids_load_device", "kxpu_table_free", "kxpu_table_rows", "kxpu_table_export", "kxpu_lookup",
-    "kxpu_lookup_device", "kxpu_names", "kxpu_comm_unique_id", "kxpu_comm_init", "kxpu_comm_destroy",
+    "kxpu_lookup_device", "kxpu_pciids_join_device", "kxpu_names", "kxpu_comm_unique_id", "kxpu_comm_init", "kxpu_comm_destroy",
     "kxpu_pciids_load_sharded", "kxpu_classify", "kxpu_cdi_emit", "kxpu_alloc_names", "kxpu_lw_encode",
 ]
 
@@ -84,6 +84,7 @@ def load_library():
         "kxpu_dev_replicate": (i32, [vp, vp, vp, sz, sz]),
         "kxpu_pinned_alloc": (i32, [vp, sz, C.POINTER(vp)]),
         "kxpu_pinned_free": (i32, [vp, vp]),
+        "kxpu_set_stage_timing": (i32, [vp, i32]),
         "kxpu_sync": (i32, [vp]),
         "kxpu_pciids_load": (i32, [vp, vp, sz, C.POINTER(vp)]),
         "kxpu_pciids_load_device": (i32, [vp, vp, sz, C.POINTER(vp)]),
@@ -92,6 +93,7 @@ def load_library():
         "kxpu_table_export": (i32, [vp, vp, vp, vp, vp, sz, C.POINTER(C.c_uint32)]),
         "kxpu_lookup": (i32, [vp, vp, vp, sz, vp]),
         "kxpu_lookup_device": (i32, [vp, vp, vp, sz, vp]),
+        "kxpu_pciids_join_device": (i32, [vp, vp, sz, vp, sz, vp, C.POINTER(vp)]),
         "kxpu_names": (i32, [vp, vp, vp, sz, vp, sz, vp, C.POINTER(sz)]),
         "kxpu_comm_unique_id": (i32, [vp]),
         "kxpu_comm_init": (i32, [vp, i32, i32, vp]),
@@ -170,6 +172,9 @@ class Kxpu:
         return ms.value
 
     # -- memory
+    def set_stage_timing(self, on):
+        self._chk(self.L.kxpu_set_stage_timing(self.ctx, 1 if on else 0))
+
     def dev_alloc(self, nbytes):
         p = C.c_void_p()
         self._chk(self.L.kxpu_dev_alloc(self.ctx, nbytes, C.byref(p)))
@@ -211,6 +216,11 @@ class Kxpu:
     def pciids_load_device(self, d_text, n):
         h = C.c_void_p()
         self._chk(self.L.kxpu_pciids_load_device(self.ctx, d_text, n, C.byref(h)))
+        return Table(self, h)
+
+    def pciids_join_device(self, d_text, n, d_keys, nq, d_rows):
+        h = C.c_void_p()
+        self._chk(self.L.kxpu_pciids_join_device(self.ctx, d_text, n, d_keys, nq, d_rows, C.byref(h)))
         return Table(self, h)
 
     def pciids_load_sharded(self, d_text, n, global_base):

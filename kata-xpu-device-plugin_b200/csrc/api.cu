@@ -104,6 +104,13 @@ extern "C" int32_t kxpu_ctx_destroy(kxpu_ctx *ctx) {
     return KXPU_OK;
 }
 
+extern "C" int32_t kxpu_set_stage_timing(kxpu_ctx *ctx, int32_t on) {
+    if (!ctx) return KXPU_E_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->stage_timing = on != 0;
+    return KXPU_OK;
+}
+
 extern "C" int32_t kxpu_last_timings(kxpu_ctx *ctx, float ms_out[KXPU_T_COUNT]) {
     if (!ctx || !ms_out) return KXPU_E_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -318,10 +325,23 @@ static int32_t launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_te
     return KXPU_OK;
 }
 
+struct KxJoin {  // optional batched join enqueued behind the finalize, in front of the host round trip
+    const uint32_t *d_keys;
+    size_t n;
+    int32_t *d_rows;
+};
+static int32_t launch_lookup(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *d_keys, size_t n, int32_t *d_rows);
+
 // Parse d_text[0..n) (global offsets base..base+n) and finalize.  check_valid=1 yields the
 // final table of a single text; 0 leaves every local candidate row for the sharded merge.
+static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned long long base,
+                                   unsigned long long carry_in, int check_valid, kxpu_table **out, const KxJoin *join);
 int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned long long base,
                        unsigned long long carry_in, int check_valid, kxpu_table **out) {
+    return kx_build_table_join(ctx, d_text, n, base, carry_in, check_valid, out, nullptr);
+}
+static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned long long base,
+                                   unsigned long long carry_in, int check_valid, kxpu_table **out, const KxJoin *join) {
     if ((reinterpret_cast<uintptr_t>(d_text) & 15u) != 0) {
         KX_SET_ERR(ctx, "device text pointer must be 16-byte aligned");
         return KXPU_E_INVALID;
@@ -400,6 +420,9 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
             rc = launch_finalize(ctx, t, d_text, n, base, check_valid);
         }
         if (rc != KXPU_OK) { table_release(ctx, t); return rc; }
+        // the join does not need anything from the host: enqueue it before the round trip below
+        // (it is simply run again if the table has to be rebuilt)
+        if (join) launch_lookup(ctx, t, join->d_keys, join->n, join->d_rows);
         cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
@@ -424,6 +447,7 @@ int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned 
             cudaMemsetAsync(&t->dev.counters[KX_C_NSEL], 0, 4, ctx->stream);
             rc = launch_finalize(ctx, t, d_text, n, base, check_valid);
             if (rc != KXPU_OK) { table_release(ctx, t); return rc; }
+            if (join) launch_lookup(ctx, t, join->d_keys, join->n, join->d_rows);
             cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
             KX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
@@ -595,6 +619,15 @@ extern "C" int32_t kxpu_pciids_load_device(kxpu_ctx *ctx, const void *d_text, si
     if (!out || (!d_text && n)) return KXPU_E_INVALID;
     kx_clear_timings(ctx);
     return kx_build_table(ctx, (const uint8_t *)d_text, n, 0, 0, 1, out);
+}
+
+extern "C" int32_t kxpu_pciids_join_device(kxpu_ctx *ctx, const void *d_text, size_t n, const uint32_t *d_keys, size_t nq,
+                                           int32_t *d_rows_out, kxpu_table **out) {
+    KX_ENTER(ctx);
+    if (!out || (!d_text && n) || (nq && (!d_keys || !d_rows_out))) return KXPU_E_INVALID;
+    kx_clear_timings(ctx);
+    const KxJoin j{d_keys, nq, d_rows_out};
+    return kx_build_table_join(ctx, (const uint8_t *)d_text, n, 0, 0, 1, out, &j);
 }
 
 extern "C" int32_t kxpu_pciids_load(kxpu_ctx *ctx, const uint8_t *text, size_t n, kxpu_table **out) {

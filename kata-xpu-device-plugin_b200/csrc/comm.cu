@@ -183,7 +183,12 @@ extern "C" int32_t kxpu_pciids_load_sharded(kxpu_ctx *ctx, const void *d_text_sh
             kx_table_release(ctx, local);
             return KXPU_E_NOMEM;
         }
-        cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE], ctx->stream);
+        if (ctx->stage_timing) cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE], ctx->stream);
+        static const bool trace = getenv("KXPU_TRACE_MERGE") != nullptr;
+        static cudaEvent_t tev[4];
+        static bool tev_ok = false;
+        if (trace && !tev_ok) { for (auto &e2 : tev) cudaEventCreate(&e2); tev_ok = true; }
+        if (trace) cudaEventRecord(tev[0], ctx->stream);
         // 2. pack the slab
         cudaMemsetAsync(d_slab, 0, sizeof(SlabHeader), ctx->stream);
         pack_rows_kernel<<<(std::max(n_rows, 1u) + 255) / 256, 256, 0, ctx->stream>>>(
@@ -192,6 +197,7 @@ extern "C" int32_t kxpu_pciids_load_sharded(kxpu_ctx *ctx, const void *d_text_sh
         ctx->launches += 2;
         if (blob_used > 0 && blob_used <= caps.blob)
             cudaMemcpyAsync(d_slab + slab_blob_off(caps), blob, blob_used, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (trace) cudaEventRecord(tev[1], ctx->stream);
         // 3. the one collective of the path
         int nrc = g_nccl.all_gather(d_slab, d_gather, sb, /*ncclUint8*/ 1, ctx->nccl_comm, ctx->stream);
         if (nrc != 0) {
@@ -201,12 +207,20 @@ extern "C" int32_t kxpu_pciids_load_sharded(kxpu_ctx *ctx, const void *d_text_sh
             kx_table_release(ctx, local);
             return KXPU_E_NCCL;
         }
+        if (trace) cudaEventRecord(tev[2], ctx->stream);
         cudaFreeAsync(d_slab, ctx->stream);
         // 4. min-merge into a fresh table (keeps d_gather: the names live there)
         kxpu_table *merged = nullptr;
         rc = kx_table_from_gather(ctx, d_gather, R, sb, caps, &merged);
-        cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE + 1], ctx->stream);
-        ctx->ev_used[KXPU_T_MERGE] = true;
+        if (ctx->stage_timing) { cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE + 1], ctx->stream); ctx->ev_used[KXPU_T_MERGE] = true; }
+        if (trace) {
+            cudaEventRecord(tev[3], ctx->stream);
+            cudaEventSynchronize(tev[3]);
+            float a = 0, b = 0, c2 = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]); cudaEventElapsedTime(&c2, tev[2], tev[3]);
+            static int calls = 0;
+            if (++calls % 8 == 0) fprintf(stderr, "[kxpu merge trace] pack %.1f us  all-gather %.1f us  merge+sync %.1f us  slab %zu B x %d\n", a * 1e3, b * 1e3, c2 * 1e3, sb, R);
+        }
         if (rc == KXPU_E_CAPACITY) {
             // some rank overflowed a slab capacity: every rank sees the same headers and retries alike
             caps.rows *= 4; caps.vendors = 65536; caps.blob *= 8;

@@ -16,6 +16,7 @@ struct kxpu_ctx {
     cudaEvent_t ev[2 * KXPU_T_COUNT] = {};
     cudaEvent_t ev_user[2] = {};
     bool ev_used[KXPU_T_COUNT] = {};
+    bool stage_timing = true;  // per-stage CUDA events (kxpu_last_timings); kxpu_set_stage_timing(ctx, 0) drops them
     uint64_t launches = 0;
     std::mutex mu;
     char err[512] = {0};
@@ -44,7 +45,10 @@ struct KxTimer {  // records a CUDA-event pair around a stage on the ctx stream
     kxpu_ctx *c;
     int idx;
     bool open = true;
-    KxTimer(kxpu_ctx *ctx, int i) : c(ctx), idx(i) { cudaEventRecord(c->ev[2 * i], c->stream); }
+    KxTimer(kxpu_ctx *ctx, int i) : c(ctx), idx(i) {
+        open = c->stage_timing;
+        if (open) cudaEventRecord(c->ev[2 * i], c->stream);
+    }
     void stop() {
         if (open) { cudaEventRecord(c->ev[2 * idx + 1], c->stream); c->ev_used[idx] = true; open = false; }
     }

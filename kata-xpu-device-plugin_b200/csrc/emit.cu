@@ -282,7 +282,7 @@ extern "C" int32_t kxpu_cdi_emit(kxpu_ctx *ctx, int32_t format, const kxpu_cdide
     E.lens = (uint32_t *)(b + o_lens); E.offs = (const unsigned long long *)(b + o_offs);
     E.out = nullptr; E.head_len = hl; E.flags = (uint32_t *)(b + o_flags);
     unsigned long long *d_part = (unsigned long long *)(b + o_part);
-    cudaEventRecord(ctx->ev[2 * KXPU_T_EMIT], ctx->stream);
+    if (ctx->stage_timing) cudaEventRecord(ctx->ev[2 * KXPU_T_EMIT], ctx->stream);
     k_cdi_len<<<(N + 1 + 255) / 256, 256, 0, ctx->stream>>>(E);
     ctx->launches++;
     kxscan::exclusive_scan<unsigned long long>(ctx, E.lens, n + 1, (unsigned long long *)(b + o_offs), d_part, nullptr);
@@ -308,8 +308,7 @@ extern "C" int32_t kxpu_cdi_emit(kxpu_ctx *ctx, int32_t format, const kxpu_cdide
             if (tl) cudaMemcpyAsync(d_out + hl + h_total, tail, tl, cudaMemcpyHostToDevice, ctx->stream);
             k_cdi_write<<<(N + EMIT_WARPS - 1) / EMIT_WARPS, EMIT_WARPS * 32, 0, ctx->stream>>>(E);
             ctx->launches++;
-            cudaEventRecord(ctx->ev[2 * KXPU_T_EMIT + 1], ctx->stream);
-            ctx->ev_used[KXPU_T_EMIT] = true;
+            if (ctx->stage_timing) { cudaEventRecord(ctx->ev[2 * KXPU_T_EMIT + 1], ctx->stream); ctx->ev_used[KXPU_T_EMIT] = true; }
             cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, ctx->stream);
             cudaFreeAsync(d_out, ctx->stream);
             e = cudaStreamSynchronize(ctx->stream);

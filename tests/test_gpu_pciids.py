@@ -317,3 +317,34 @@ def test_structural_byte_fuzz(kx, oracle):
             body = b"".join(p + b"\n%04x  V\n\t%04x  D\n" % (int(rng.integers(0, 6)), int(rng.integers(0, 6))) for p in pieces)
         keys = [(int(rng.integers(0, 6)) << 16) | int(rng.integers(0, 6)) for _ in range(16)]
         check_text(kx, oracle, body, extra_keys=keys)
+
+
+def test_join_device_equals_load_then_lookup(kx, pci_text, oracle_rows, workloads):
+    """kxpu_pciids_join_device == kxpu_pciids_load_device + kxpu_lookup_device (also when the
+    table has to grow and the join is replayed)."""
+    for text in (pci_text, b"abcd  Big\n" + b"".join(b"\t%04x  x\n" % d for d in range(40000))):
+        buf = np.frombuffer(text, np.uint8)
+        d_text = kx.dev_alloc(len(buf))
+        kx.upload(d_text, buf)
+        t0 = kx.pciids_load_device(d_text, len(buf))
+        keys, _, _ = kx.table_export(t0)
+        q = workloads.make_queries(keys, 4096, 11)
+        d_q, d_r = kx.dev_alloc(q.nbytes), kx.dev_alloc(q.nbytes)
+        kx.upload(d_q, q)
+        kx.lookup_device(t0, d_q, len(q), d_r)
+        want = kx.download(d_r, q.nbytes, np.int32)
+        kx.upload(d_r, np.full(len(q), -7, np.int32))
+        t1 = kx.pciids_join_device(d_text, len(buf), d_q, len(q), d_r)
+        got = kx.download(d_r, q.nbytes, np.int32)
+        k1, o1, r1 = kx.table_export(t1)
+        k0, o0, r0 = kx.table_export(t0)
+        assert t1.rows == t0.rows and np.array_equal(k0, k1) and np.array_equal(o0, o1)
+        # row handles belong to their table: compare the lines they stand for
+        line0 = dict(zip(r0.tolist(), o0.tolist()))
+        line1 = dict(zip(r1.tolist(), o1.tolist()))
+        assert [line0.get(x, -1) for x in want.tolist()] == [line1.get(x, -1) for x in got.tolist()]
+        assert (want >= 0).any() and (got != -7).all()
+        for t in (t0, t1):
+            t.free()
+        for d in (d_text, d_q, d_r):
+            kx.dev_free(d)
