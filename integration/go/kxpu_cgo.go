@@ -1,23 +1,8 @@
-# INTEGRATION — dropping libkxpu.so under the Go plugin
+// kxpu_cgo.go -- the cgo shim of INTEGRATION.md as a file: drop it into pkg/device_plugin of the
+// reference next to device_plugin.go (build tag keeps the stock CPU path selectable).
+// NOT compiled in this repository: the build image has no Go toolchain.
+//go:build kxpu
 
-The reference (`Apokleos/kata-xpu-device-plugin`) is a single Go binary with no FFI.  The
-B200 path is cut in **under** its package `pkg/device_plugin` with one cgo file; the gRPC
-surface (Register / ListAndWatch / Allocate), the CDI file name and format, the DaemonSet
-(`deploy/kata-xpu-device-plugin.yaml`) and the container command stay byte-identical.  The
-Go toolchain is absent from this build image, so the shim below is shown, not compiled; the
-same calls are exercised through `kata-xpu-device-plugin_b200/host/device_plugin.cpp` (C++
-mirror of the package) and `binding.py` (ctypes) in `tests/`.
-
-Ship: `libkxpu.so` (built by `make -C kata-xpu-device-plugin_b200`, cudart linked
-statically; NCCL only `dlopen`ed for multi-GPU) next to the binary, `include/kxpu.h`.
-Image: the Dockerfile already bases on `nvcr.io/nvidia/cuda:12.5.1-base` (Dockerfile:27-31);
-the pod needs a B200 visible to the plugin container (`NVIDIA_VISIBLE_DEVICES`), which is a
-deployment change outside the manifest's four mounts.  Any `kxpu_*` failure at start-up is
-`log.Fatalf`: there is no CPU fallback.
-
-## cgo shim (new file `pkg/device_plugin/kxpu_cgo.go`)
-
-```go
 package device_plugin
 
 /*
@@ -152,36 +137,3 @@ func (k *kxpu) allocNames(idx []uint64) ([]string, error) {
 	}
 	return out, err
 }
-```
-
-## The six call sites (SURVEY §8(b)) in the reference sources
-
-| Site | Reference | Change |
-|---|---|---|
-| S1 | `createIommuDeviceMap`, `device_plugin.go:132-179` | the `filepath.Walk` callback keeps its reads (`readIDFromFile`, `readLink`) but only appends one `C.kxpu_devrec` per non-directory entry (raw `vendor`/`device` bytes, link basenames, `KXPU_REC_*` flags for failed reads) — exactly `host/device_plugin.cpp::walkDir`; after the walk `k.classify(recs)` fills `iommuMap` (`group_ids/off/members` + `accept_index`) and `deviceMap` (`dev_ids/off/groups`). |
-| S2 | `getDeviceName`, `device_plugin.go:99,208-259` | `k.loadPciIds(pciIdsFilePath)` once in `InitiateDevicePlugin`; `createDevicePlugins` calls `k.deviceNames(ids)` for all `deviceMap` keys in one batch; `""` still falls back to the raw id (:100-103).  With text and keys already in device memory, `kxpu_pciids_join_device` does parse + join in one call (no host round trip between the two). |
-| S3 | `generateCDISpec` + `Save`, `device_plugin.go:55-80`, `cdi/spec.go:85-127` | build `[]C.kxpu_cdidev` in ascending `index`, `doc := k.cdiEmit(0, devs)`, `os.WriteFile(cdiConfigPath+"cdi-vfio-xxxx.yaml", doc, 0644)`; errors are printed and swallowed as before. |
-| S4 | device list build, `device_plugin.go:91-98` | `pluginapi.Device{ID: strconv(dev_groups[j]), Health: Healthy}` for `j` in `dev_off[d]..dev_off[d+1]`. |
-| S5 | `Allocate` → `updateResponseForCDI`, `generic_device_plugin.go:274-299,340` | the per-device re-validation (`readLink`/`readIDFromFile`, :329-338) stays; `k.allocNames(devIndexes)` replaces the `QualifiedName` loop; `Envs` is overwritten as before (:348-350).  `kxpu_ctx` is mutex-protected, so concurrent grpc-go handlers may share it. |
-| S6 | seams `basePath`, `pciIdsFilePath`, `readLink`, `readIDFromFile`, `returnIommuMap`, `startDevicePlugin` | untouched; the Go tests a maintainer adds drive them exactly like `tests/test_host.py` drives the C++ mirror on a fake sysfs tree (entries are symlinks, see `tests/fake_sysfs.py`). |
-
-Optional: `ListAndWatch` may send pre-encoded bytes from `kxpu_lw_encode` through a raw-bytes
-grpc codec (generic_device_plugin.go:224); otherwise it keeps `s.Send(&ListAndWatchResponse{…})`.
-
-## Multi-GPU (only when the text outgrows one GPU)
-
-One rank per GPU: `kxpu_comm_unique_id` on rank 0, broadcast the 128 bytes by any means,
-`kxpu_comm_init(ctx, nranks, rank, id)`, split the text where a top-level line starts
-(`kata-xpu-device-plugin_b200/sharding.py::plan_shards` shows the rule), upload each shard,
-`kxpu_pciids_load_sharded(ctx, d_shard, n, global_base, &table)` (collective, one
-`ncclAllGather`).  Every rank ends with the same table.
-
-## Go tests to add when a toolchain is available (SURVEY §8(c), last row)
-
-Shipped uncompiled in `integration/go/`: `kxpu_cgo.go` (the shim above as a file, build tag
-`kxpu`) and `kxpu_parity_test.go` (reference functions against this repository's fixtures).
-
-Point `basePath`/`pciIdsFilePath` at the fixtures of `tests/` and diff: names for all 1 859
-NVIDIA ids (`tests/golden/golden.json: nvidia_dump_sha256`), YAML for BDFs `0000:01:00.0`
-(quoted) and `0000:c1:00.0` (plain), JSON via `Save(…,"JSON")` against
-`tests/golden/cfg1.{yaml,json}`.  That run would turn "parity unpinned" into "pinned".
