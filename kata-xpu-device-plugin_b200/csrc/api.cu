@@ -227,7 +227,8 @@ static int32_t table_alloc(kxpu_ctx *ctx, uint32_t cap, uint32_t blob_cap, uint3
     size_t o_trunc = off;       off = align_up(off + 8, 256);
     size_t ff_bytes = off;
     size_t o_counters = off;    off = align_up(off + KX_C_COUNT * 4, 256);
-    size_t o_tiles = off;       off = align_up(off + ((size_t)num_tiles + 64) * 8, 256);
+    // v1-v4: one zeroed status word per tile; v5: up to 24 B of (never zeroed) range words per chunk
+    size_t o_tiles = off;       off = align_up(off + ((size_t)num_tiles + 64) * (zero_tiles ? 8 : 24), 256);
     size_t zero_bytes = off - ff_bytes;
     size_t o_row_of_slot = off; off = align_up(off + slots * 4, 256);
     size_t o_row_key = off;     off = align_up(off + slots * 4, 256);
@@ -363,19 +364,22 @@ static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t 
                 kxparse5::Params5 P;
                 P.text = d_text; P.n = n; P.base = base; P.num_chunks = num_tiles;
                 P.tma_limit = n >= (size_t)kxparse2::STG_BYTES ? (uint32_t)((n - kxparse2::STG_BYTES) / kxparse2::CW) + 1u : 0u;
-                P.num_ranges = (num_tiles + kxparse5::RCH5 - 1) / kxparse5::RCH5;
+                int per_sm = 0;
+                const size_t smem = sizeof(kxparse5::WarpSmem5) * kxparse2::WARPS;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kxparse5::parse_kernel_v5, kxparse2::NT, smem);
+                if (per_sm < 1) per_sm = 1;
+                // ranges of 8 chunks; shorter ones when the text is too small to give every warp a range
+                const uint32_t wave_warps = (uint32_t)per_sm * ctx->sm_count * kxparse2::WARPS;
+                P.rch = std::min<uint32_t>(std::max<uint32_t>(num_tiles / wave_warps, 1u), kxparse5::RCH5_MAX);
+                P.num_ranges = (num_tiles + P.rch - 1) / P.rch;
                 P.range_state = t->tile_state;                            // [num_ranges]
                 P.range_carry = t->tile_state + P.num_ranges;             // [num_ranges]
                 P.lead = (uint32_t *)(t->tile_state + 2 * P.num_ranges);  // [num_ranges]
                 P.tasks = P.lead + P.num_ranges;                          // [num_tiles]
                 P.tab = t->dev; P.carry_in = carry_in;
-                int per_sm = 0;
-                const size_t smem = sizeof(kxparse5::WarpSmem5) * kxparse2::WARPS;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kxparse5::parse_kernel_v5, kxparse2::NT, smem);
-                if (per_sm < 1) per_sm = 1;
-                // persistent grid; every warp holds two range tickets at a time
+                // persistent grid, at most one warp per range
                 uint32_t grid = (uint32_t)per_sm * ctx->sm_count;
-                const uint32_t need = (P.num_ranges + 2 * kxparse2::WARPS - 1) / (2 * kxparse2::WARPS);
+                const uint32_t need = (P.num_ranges + kxparse2::WARPS - 1) / kxparse2::WARPS;
                 if (grid > need) grid = need;
                 kxparse5::parse_kernel_v5<<<grid, kxparse2::NT, smem, ctx->stream>>>(P);
                 KX_LAUNCHED(ctx);

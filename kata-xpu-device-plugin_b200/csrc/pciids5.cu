@@ -4,7 +4,8 @@
 // (profiles/r01_parse_v4d_*): 8 % of all instructions were warps polling the CTA barrier that
 // orders the per-chunk status words, and the per-iteration bookkeeping of the shared ticket /
 // phase-B pipeline cost as much as the newline masks.  v5 removes the sharing:
-//   * the text is cut into RANGES of 8 chunks (16 KiB) handed out to WARPS by ticket (a static
+//   * the text is cut into RANGES of 8 chunks (16 KiB; fewer for texts too small to give every
+//     warp of the grid a range) handed out to WARPS by ticket (a static
 //     split leaves the SM half empty at the end: the issue arbiter favours some warps, they
 //     finish early); a warp streams its ranges 2 KiB at a time through a private 3-stage ring
 //     of 1-D TMA bulk copies (cp.async.bulk + mbarrier) -- no CTA barrier, no shared status;
@@ -39,9 +40,8 @@ using kxparse4::stage_chunk_manual;
 using kxparse4::tma_load_a;
 
 constexpr int STAGES5 = 3;
-constexpr int RCH5 = 8;  // chunks per range (16 KiB)
+constexpr int RCH5_MAX = 8;  // chunks per range (16 KiB); fewer for small texts so that every warp gets a range
 constexpr int RES_WARPS = 8;
-static_assert(RCH5 > STAGES5, "the prefetch cursor may run at most one range ahead");
 
 struct WarpSmem5 {
     alignas(16) uint8_t stage[STAGES5][STG_BYTES];
@@ -53,6 +53,7 @@ struct Params5 {
     unsigned long long n, base;
     uint32_t num_chunks;
     uint32_t tma_limit;               // chunks [0, tma_limit) can be staged with one bulk copy of STG_BYTES
+    uint32_t rch;                     // chunks per range, 1..RCH5_MAX
     uint32_t num_ranges;
     unsigned long long *range_state;  // [num_ranges] inclusive carry at the end of the range (ST_*/CV_*)
     uint32_t *lead;                   // [num_ranges] leading chunks whose head lines wait for the resolve kernels
@@ -136,13 +137,9 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
         for (int s = 0; s < STAGES5; s++) mbar_init(&W[w].bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // two ranges in flight per warp: the current one and the next (its ticket is drawn one range early)
     uint32_t tk = 0;
-    if (lane == 0) {
-        tk = atomicAdd(&P.tab.counters[KX_C_TICKET], 2u);
-    }
-    tk = __shfl_sync(0xffffffffu, tk, 0);
-    uint32_t r = tk, r_next = tk + 1u;
+    if (lane == 0) tk = atomicAdd(&P.tab.counters[KX_C_TICKET], 1u);
+    uint32_t r = __shfl_sync(0xffffffffu, tk, 0);
     if (r >= P.num_ranges) return;
 
     // shared-window addresses (see kxparse4::lds128)
@@ -160,16 +157,14 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
             tma_load_a(a_stage0 + s * (uint32_t)STG_BYTES, P.text + (unsigned long long)g * CW, STG_BYTES, a_bar0 + 8u * s, pol);
         }
     };
-    if (lane == 0) {
-        issue(r * RCH5, 0);
-        issue(r * RCH5 + 1u, 1);
-        issue(r * RCH5 + 2u, 2);
-    }
+    const uint32_t rch = P.rch;
+    bool staged = false;  // the first chunks of the coming range are already on their way
 
     uint32_t phase_bits = 0, s = 0;
     for (;;) {
-        // ticket of the range after next; consumed (shuffled) late in this range
-        uint32_t tk2 = 0;
+        // ticket of the next range, drawn one range early; looked at (shuffled) late in this range
+        uint32_t tk2 = 0, r_next = 0xffffffffu;
+        bool have_next = false;
         if (lane == 0) tk2 = atomicAdd(&P.tab.counters[KX_C_TICKET], 1u);
         // carry along the range: the governing line at the start of the next chunk as a status word
         // (LS_* of pciids3.cu; 0 = not known) plus the chunk that holds the line (0xffffffff = the
@@ -179,10 +174,18 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
             rc_x = LS_PUB | (((P.carry_in & CV_HAS_TOP) && (P.carry_in & CV_VOK)) ? (LS_TOP | LS_VOK) : 0u);
             rc_g = 0xffffffffu;
         }
-        uint32_t lead = r == 0u ? 0u : (uint32_t)RCH5;  // chunks whose head lines nobody can judge yet
-        const uint32_t gb = r * RCH5;
-        const uint32_t cnt = P.num_chunks - gb < (uint32_t)RCH5 ? P.num_chunks - gb : (uint32_t)RCH5;
+        uint32_t lead = r == 0u ? 0u : rch;  // chunks whose head lines nobody can judge yet
+        const uint32_t gb = r * rch;
+        const uint32_t cnt = P.num_chunks - gb < rch ? P.num_chunks - gb : rch;
+        if (!staged && lane == 0) {
+            for (uint32_t j = 0; j < (uint32_t)STAGES5 && j < cnt; j++) issue(gb + j, (s + j) % (uint32_t)STAGES5);
+        }
+        staged = false;
         for (uint32_t i = 0; i < cnt; i++) {
+            if (!have_next && rch > (uint32_t)STAGES5 && i + (uint32_t)STAGES5 >= rch) {
+                r_next = __shfl_sync(0xffffffffu, tk2, 0);
+                have_next = true;
+            }
             const uint32_t g = gb + i;
             const uint32_t st = a_stage0 + s * (uint32_t)STG_BYTES;
             const unsigned long long cbase = P.base + (unsigned long long)g * CW;
@@ -333,12 +336,19 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
             if ((bal0 | bal1) == 0u && n_rel > (uint32_t)CW && __reduce_or_sync(0xffffffffu, rawnl) == 0u && lane == 0)
                 atomicOr(&P.tab.counters[KX_C_LONGLINE_HINT], 1u);
 
-            // the stage is free: prefetch the chunk three steps ahead into it (this range or the next)
+            // the stage is free: prefetch the chunk three steps ahead into it -- of this range, or (ranges
+            // longer than the ring only) of the next one
             __syncwarp();
-            if (lane == 0) {
+            {
                 const uint32_t fi = i + (uint32_t)STAGES5;
-                const uint32_t fg = fi < (uint32_t)RCH5 ? g + (uint32_t)STAGES5 : (r_next < P.num_ranges ? r_next * RCH5 + (fi - (uint32_t)RCH5) : 0xffffffffu);
-                issue(fg, s);
+                uint32_t fg = 0xffffffffu;
+                if (fi < rch) {
+                    fg = g + (uint32_t)STAGES5;
+                } else if (rch > (uint32_t)STAGES5 && cnt == rch && r_next < P.num_ranges) {
+                    fg = r_next * rch + (fi - rch);
+                    staged = true;
+                }
+                if (lane == 0) issue(fg, s);
             }
             s = s == (uint32_t)STAGES5 - 1u ? 0u : s + 1u;
         }
@@ -355,8 +365,8 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
             P.range_state[r] = v;
             P.lead[r] = lead < cnt ? lead : cnt;
         }
+        if (!have_next) r_next = __shfl_sync(0xffffffffu, tk2, 0);
         r = r_next;
-        r_next = __shfl_sync(0xffffffffu, tk2, 0);
         if (r >= P.num_ranges) break;
     }
 }
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(256) resolve_ranges_kernel(const Params5 P) {
     if (!alive) return;
     P.range_carry[rr] = carry;
     const uint32_t at = atomicAdd(&P.tab.counters[KX_C_DEFER], nlead);
-    for (uint32_t j = 0; j < nlead; j++) P.tasks[at + j] = rr * RCH5 + j;
+    for (uint32_t j = 0; j < nlead; j++) P.tasks[at + j] = rr * P.rch + j;
 }
 
 // Resolve, step 2: one warp per queued chunk stages it again and folds its head lines (the
@@ -421,7 +431,7 @@ __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Pa
         } else {
             n_rel = stage_chunk_manual(P.text, P.n, gg, lane, stg[w]);
         }
-        const unsigned long long cc = P.range_carry[gg / RCH5];
+        const unsigned long long cc = P.range_carry[gg / P.rch];
         const uint32_t key_hi = ((uint32_t)(cc >> 44) & 0xffffu) << 16;
         const unsigned long long anchor = cc & CV_ANCHOR_MASK;
         uint32_t kh[2], th[2], rawnl;
