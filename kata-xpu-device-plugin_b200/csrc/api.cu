@@ -87,6 +87,8 @@ extern "C" int32_t kxpu_ctx_create(int32_t ordinal, kxpu_ctx **out) {
     cudaFuncSetAttribute(kxparse5::parse_kernel_v5, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(sizeof(kxparse5::WarpSmem5) * kxparse2::WARPS));
     c->parse_version = (pv && pv[0] >= '1' && pv[0] <= '5') ? pv[0] - '0' : 5;
+    const char *fr = getenv("KXPU_RCH");
+    c->force_rch = (fr && fr[0] >= '1' && fr[0] <= '8' && !fr[1]) ? fr[0] - '0' : 0;
     *out = c;
     return KXPU_OK;
 }
@@ -371,6 +373,7 @@ static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t 
                 // ranges of 8 chunks; shorter ones when the text is too small to give every warp a range
                 const uint32_t wave_warps = (uint32_t)per_sm * ctx->sm_count * kxparse2::WARPS;
                 P.rch = std::min<uint32_t>(std::max<uint32_t>(num_tiles / wave_warps, 1u), kxparse5::RCH5_MAX);
+                if (ctx->force_rch) P.rch = (uint32_t)ctx->force_rch;
                 P.num_ranges = (num_tiles + P.rch - 1) / P.rch;
                 P.range_state = t->tile_state;                            // [num_ranges]
                 P.range_carry = t->tile_state + P.num_ranges;             // [num_ranges]

@@ -348,3 +348,21 @@ def test_join_device_equals_load_then_lookup(kx, pci_text, oracle_rows, workload
             t.free()
         for d in (d_text, d_q, d_r):
             kx.dev_free(d)
+
+
+@pytest.mark.parametrize("rch", [1, 2, 3, 4, 5, 7, 8])
+def test_every_range_length(rch, oracle, pci_text, monkeypatch):
+    """The parse kernel cuts the text into ranges of 1..8 chunks depending on its size
+    (KXPU_RCH forces one): the prefetch ring, the carry and the resolve pass must agree for all."""
+    import kxpu_b200 as K
+    monkeypatch.setenv("KXPU_RCH", str(rch))
+    k = K.Kxpu(0)
+    try:
+        rng = np.random.default_rng(rch)
+        check_text(k, oracle, pci_text[:400003])
+        check_text(k, oracle, pci_text[:pci_text.rfind(b"\n", 0, 120000) + 1] * 5)
+        check_text(k, oracle, _big_random_text(rng, 9000, 120, 0.4), extra_keys=[0x00010001, 0x00630000])
+        for n in (2047, 2048, 2049, 2048 * rch, 2048 * rch + 1, 2048 * rch * 3 - 1):
+            check_text(k, oracle, pci_text[:n])
+    finally:
+        k.close()
