@@ -3,18 +3,24 @@
 #include "device_plugin.hpp"
 
 #include <dirent.h>
+#include <poll.h>
+#include <sys/inotify.h>
 #include <sys/stat.h>
 #include <unistd.h>
+
+#include <fcntl.h>
 
 #include <algorithm>
 #include <cerrno>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 
 namespace device_plugin {
 
 static const char *kDevicePluginPath = "/var/lib/kubelet/device-plugins/";  // pluginapi.DevicePluginPath
 static const char *kHealthy = "Healthy";                                     // pluginapi.Healthy
+static const char *kUnhealthy = "Unhealthy";                                 // pluginapi.Unhealthy
 static const char *kK8SCDIVendorClass = "KUBERNETES_CDI_VENDOR_CLASS";       // generic_device_plugin.go:29
 static const char *kCdiVendorClass = "nvidia.com/gpu";                       // generic_device_plugin.go:30
 
@@ -66,6 +72,46 @@ Plugin::~Plugin() {
     if (table_) kxpu_table_free(ctx_, table_);
 }
 
+// The body of the walk callback for one non-directory entry (device_plugin.go:141-175, the reads
+// only): raw bytes of `vendor` / `device`, basenames of the `driver` / `iommu_group` links.
+template <typename ReadID, typename ReadLnk>
+static Error leafRecord(const std::string &name, ReadID readID, ReadLnk readLnk, kxpu_devrec &r) {
+    memset(&r, 0, sizeof r);
+    std::string s;
+    bool vendor_ok = readID("vendor", s);
+    if (!vendor_ok) {
+        r.flags |= KXPU_REC_VENDOR_ERR;  // "Could not get vendor ID for device" -> skipped
+        strncpy(r.bdf, name.c_str(), sizeof r.bdf - 1);
+        return Error();
+    }
+    if (name.size() > sizeof r.bdf - 1) return fail("PCI address longer than 15 bytes: " + name);
+    memcpy(r.bdf, name.data(), name.size());
+    r.vendor_len = (uint8_t)std::min<size_t>(s.size(), 255);
+    memcpy(r.vendor_txt, s.data(), std::min<size_t>(s.size(), 8));
+    if (readLnk("driver", s)) {
+        memcpy(r.driver, s.data(), std::min<size_t>(s.size(), sizeof r.driver - 1));
+    } else {
+        r.flags |= KXPU_REC_DRIVER_ERR;
+    }
+    if (readLnk("iommu_group", s)) {
+        bool dec = !s.empty() && s.size() <= 10;
+        unsigned long long v = 0;
+        for (char c : s) { if (c < '0' || c > '9') dec = false; else v = v * 10 + (unsigned)(c - '0'); }
+        if (!dec || v >= 0xFFFFFFFFull || (s.size() > 1 && s[0] == '0'))
+            return fail("iommu_group of " + name + " is not a canonical decimal number: " + s);
+        r.iommu_group = (uint32_t)v;
+    } else {
+        r.flags |= KXPU_REC_IOMMU_ERR;
+    }
+    if (readID("device", s)) {
+        r.device_len = (uint8_t)std::min<size_t>(s.size(), 255);
+        memcpy(r.device_txt, s.data(), std::min<size_t>(s.size(), 8));
+    } else {
+        r.flags |= KXPU_REC_DEVICE_ERR;
+    }
+    return Error();
+}
+
 // filepath.Walk(basePath, ...) (device_plugin.go:132): lexical order, os.Lstat (symlinks are not
 // followed, so a real sysfs entry is "not a directory"), directories are descended into and
 // reported as "Not a device" (:137-140).
@@ -91,40 +137,10 @@ static Error walkDir(Plugin &p, const std::string &path, const std::string &name
     // one raw record per non-directory entry; every read goes through the seams and is keyed by
     // info.Name() under basePath exactly like :142,:151,:157,:164
     kxpu_devrec r;
-    memset(&r, 0, sizeof r);
-    std::string s;
-    bool vendor_ok = p.readIDFromFile(p.basePath, name, "vendor", s);
-    if (!vendor_ok) {
-        r.flags |= KXPU_REC_VENDOR_ERR;  // "Could not get vendor ID for device" -> skipped
-        strncpy(r.bdf, name.c_str(), sizeof r.bdf - 1);
-        recs.push_back(r);
-        return Error();
-    }
-    if (name.size() > sizeof r.bdf - 1) return fail("PCI address longer than 15 bytes: " + name);
-    memcpy(r.bdf, name.data(), name.size());
-    r.vendor_len = (uint8_t)std::min<size_t>(s.size(), 255);
-    memcpy(r.vendor_txt, s.data(), std::min<size_t>(s.size(), 8));
-    if (p.readLink(p.basePath, name, "driver", s)) {
-        memcpy(r.driver, s.data(), std::min<size_t>(s.size(), sizeof r.driver - 1));
-    } else {
-        r.flags |= KXPU_REC_DRIVER_ERR;
-    }
-    if (p.readLink(p.basePath, name, "iommu_group", s)) {
-        bool dec = !s.empty() && s.size() <= 10;
-        unsigned long long v = 0;
-        for (char c : s) { if (c < '0' || c > '9') dec = false; else v = v * 10 + (unsigned)(c - '0'); }
-        if (!dec || v >= 0xFFFFFFFFull || (s.size() > 1 && s[0] == '0'))
-            return fail("iommu_group of " + name + " is not a canonical decimal number: " + s);
-        r.iommu_group = (uint32_t)v;
-    } else {
-        r.flags |= KXPU_REC_IOMMU_ERR;
-    }
-    if (p.readIDFromFile(p.basePath, name, "device", s)) {
-        r.device_len = (uint8_t)std::min<size_t>(s.size(), 255);
-        memcpy(r.device_txt, s.data(), std::min<size_t>(s.size(), 8));
-    } else {
-        r.flags |= KXPU_REC_DEVICE_ERR;
-    }
+    Error e = leafRecord(name,
+                         [&](const char *prop, std::string &out) { return p.readIDFromFile(p.basePath, name, prop, out); },
+                         [&](const char *link, std::string &out) { return p.readLink(p.basePath, name, link, out); }, r);
+    if (e) return e;
     recs.push_back(r);
     return Error();
 }
@@ -133,6 +149,107 @@ Error Plugin::gatherRecords(std::vector<kxpu_devrec> &recs) {
     recs.clear();
     size_t slash = basePath.find_last_of('/');
     return walkDir(*this, basePath, slash == std::string::npos ? basePath : basePath.substr(slash + 1), recs);
+}
+
+// ---------------------------------------------------------------------------- SURVEY 8(f) row 2
+// Batched sysfs ingestion: the same records as gatherRecords, but the entries of basePath are read
+// with paths RELATIVE to one directory descriptor (openat / readlinkat on "<bdf>/vendor": no lstat per
+// entry -- getdents64 already says what is a directory --, no absolute path resolution, no FILE
+// buffering) and by several threads, each filling its own slice of the record table, so that S1 ends
+// in one contiguous table ready for a single H2D copy.  Only with the default seams; real directories
+// under basePath (never on sysfs) go through the generic walk at their position.
+Error Plugin::gatherRecordsFast(std::vector<kxpu_devrec> &recs, unsigned threads) {
+    recs.clear();
+    struct stat sb;
+    if (lstat(basePath.c_str(), &sb) != 0) return fail("Error accessing file path \"" + basePath + "\": " + strerror(errno));
+    // the fast reads bypass the seams: only when nobody replaced them (tests do, device_plugin.go:38-39)
+    using SeamFn = bool (*)(const std::string &, const std::string &, const std::string &, std::string &);
+    SeamFn const *rl = readLink.target<SeamFn>(), *ri = readIDFromFile.target<SeamFn>();
+    const bool defaultSeams = rl && *rl == readLinkFunc && ri && *ri == readIDFromFileFunc;
+    if (!S_ISDIR(sb.st_mode) || !defaultSeams) return gatherRecords(recs);
+    int basefd = open(basePath.c_str(), O_RDONLY | O_DIRECTORY | O_CLOEXEC);
+    if (basefd < 0) return fail("Error accessing file path \"" + basePath + "\": " + strerror(errno));
+    DIR *d = fdopendir(dup(basefd));
+    if (!d) { close(basefd); return fail("Error accessing file path \"" + basePath + "\": " + strerror(errno)); }
+    struct Ent { std::string name; bool dir; };
+    std::vector<Ent> ents;
+    while (struct dirent *de = readdir(d)) {
+        if (strcmp(de->d_name, ".") == 0 || strcmp(de->d_name, "..") == 0) continue;
+        bool isdir = de->d_type == DT_DIR;
+        if (de->d_type == DT_UNKNOWN) {  // file systems without d_type: one fstatat, still no path walk
+            struct stat es;
+            isdir = fstatat(basefd, de->d_name, &es, AT_SYMLINK_NOFOLLOW) == 0 && S_ISDIR(es.st_mode);
+        }
+        ents.push_back(Ent{de->d_name, isdir});
+    }
+    closedir(d);
+    std::sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.name < b.name; });
+
+    const size_t N = ents.size();
+    std::vector<kxpu_devrec> flat(N);
+    std::vector<Error> errs(N);
+    auto readID = [&](const std::string &name, const char *prop, std::string &out) {
+        const std::string rel = name + "/" + prop;
+        int fd = openat(basefd, rel.c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd < 0) {
+            fprintf(stderr, "Could not read %s for device %s: %s\n", prop, name.c_str(), strerror(errno));
+            return false;
+        }
+        char buf[256];
+        size_t got = 0;
+        for (;;) {  // os.ReadFile reads to EOF
+            ssize_t k = read(fd, buf + got, sizeof buf - got);
+            if (k < 0) { close(fd); return false; }
+            if (k == 0) break;
+            got += (size_t)k;
+            if (got == sizeof buf) break;
+        }
+        close(fd);
+        out.assign(buf, got);
+        return true;
+    };
+    auto readLnk = [&](const std::string &name, const char *link, std::string &out) {
+        const std::string rel = name + "/" + link;
+        char buf[4096];
+        ssize_t k = readlinkat(basefd, rel.c_str(), buf, sizeof buf - 1);
+        if (k < 0) {
+            fprintf(stderr, "Could not read link %s for device %s: %s\n", link, name.c_str(), strerror(errno));
+            return false;
+        }
+        std::string target(buf, (size_t)k);
+        size_t slash = target.find_last_of('/');
+        out = slash == std::string::npos ? target : target.substr(slash + 1);
+        return true;
+    };
+    auto work = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            if (ents[i].dir) continue;
+            const std::string &name = ents[i].name;
+            errs[i] = leafRecord(name, [&](const char *prop, std::string &out) { return readID(name, prop, out); },
+                                 [&](const char *link, std::string &out) { return readLnk(name, link, out); }, flat[i]);
+        }
+    };
+    if (threads == 0) threads = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    threads = (unsigned)std::min<size_t>(threads, std::max<size_t>(N / 64, 1));
+    if (threads <= 1) {
+        work(0, N);
+    } else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < threads; t++) pool.emplace_back(work, N * t / threads, N * (t + 1) / threads);
+        for (auto &th : pool) th.join();
+    }
+    close(basefd);
+    // assemble in walk order; the first error in walk order wins, like the sequential walk
+    for (size_t i = 0; i < N; i++) {
+        if (ents[i].dir) {
+            Error e = walkDir(*this, basePath + "/" + ents[i].name, ents[i].name, recs);
+            if (e) return e;
+        } else {
+            if (errs[i]) return errs[i];
+            recs.push_back(flat[i]);
+        }
+    }
+    return Error();
 }
 
 static std::string devIdString(uint64_t packed) {
@@ -147,7 +264,7 @@ Error Plugin::createIommuDeviceMap() {
     iommuMap.clear();   // :127
     deviceMap.clear();  // :128
     std::vector<kxpu_devrec> recs;
-    Error e = gatherRecords(recs);
+    Error e = gatherRecordsFast(recs);  // same records as gatherRecords (falls back to it when a seam was replaced)
     if (e) { fprintf(stderr, "%s\n", e.message.c_str()); }  // Walk's error is ignored by the reference (:132)
     const size_t n = recs.size();
     std::vector<uint32_t> accept(n), gids(n), goff(n + 1), gmem(n), doff(n + 1), dgrp(n);
@@ -343,6 +460,84 @@ Error Plugin::ListAndWatchBytes(const GenericDevicePlugin &dp, std::vector<uint8
     return Error();
 }
 
+// ---------------------------------------------------------------------------- health (row 3 of SURVEY 8(f))
+HealthWatcher::HealthWatcher(GenericDevicePlugin &dp, bool watchCreates) : dp_(dp), watchCreates_(watchCreates) {}
+
+HealthWatcher::~HealthWatcher() {
+    if (fd_ >= 0) close(fd_);
+}
+
+// filepath.Join(path, dev.ID): one separator, no trailing one
+static std::string joinPath(const std::string &dir, const std::string &name) {
+    if (dir.empty()) return name;
+    return dir.back() == '/' ? dir + name : dir + "/" + name;
+}
+
+Error HealthWatcher::start() {
+    fd_ = inotify_init1(IN_NONBLOCK | IN_CLOEXEC);  // fsnotify.NewWatcher (:396)
+    if (fd_ < 0) return fail(std::string("Unable to create fsnotify watcher: ") + strerror(errno));
+    // fsnotify's inotify backend adds every path with this mask; only the ops healthCheck looks at matter
+    const uint32_t mask = IN_DELETE_SELF | IN_MOVE_SELF | IN_ATTRIB | IN_MODIFY;
+    for (const Device &dev : dp_.devs) {  // :421-430
+        const std::string devicePath = joinPath(dp_.devicePath, dev.ID);
+        int wd = inotify_add_watch(fd_, devicePath.c_str(), mask);
+        if (wd < 0) return fail("Unable to add device path to fsnotify watcher: " + devicePath + ": " + strerror(errno));
+        wdToId_[wd] = dev.ID;
+    }
+    if (watchCreates_) {
+        dirWd_ = inotify_add_watch(fd_, dp_.devicePath.c_str(), IN_CREATE | IN_MOVED_TO);
+        if (dirWd_ < 0) return fail("Unable to add device directory to fsnotify watcher: " + dp_.devicePath + ": " + strerror(errno));
+    }
+    return Error();
+}
+
+// ListAndWatch's loops over dpi.devs (:230-234, :239-243): every dev with that ID
+int HealthWatcher::setHealth(const std::string &id, const char *health) {
+    int changed = 0;
+    for (Device &d : dp_.devs)
+        if (d.ID == id && d.Health != health) { d.Health = health; changed++; }
+    return changed;
+}
+
+int HealthWatcher::poll(int timeout_ms) {
+    if (fd_ < 0) return -1;
+    struct pollfd pfd = {fd_, POLLIN, 0};
+    int pr = ::poll(&pfd, 1, timeout_ms);
+    if (pr < 0) return errno == EINTR ? 0 : -1;
+    if (pr == 0) return 0;
+    int changed = 0;
+    alignas(struct inotify_event) char buf[16384];
+    for (;;) {
+        ssize_t n = read(fd_, buf, sizeof buf);
+        if (n <= 0) break;  // EAGAIN: queue drained
+        for (char *p = buf; p < buf + n;) {
+            const struct inotify_event *ev = reinterpret_cast<const struct inotify_event *>(p);
+            p += sizeof(struct inotify_event) + ev->len;
+            events_++;
+            if (ev->wd == dirWd_ && ev->len > 0) {
+                // fsnotify.Create of devicePath/<name> (:441-443)
+                const std::string name(ev->name);
+                for (const Device &d : dp_.devs)
+                    if (d.ID == name) {
+                        changed += setHealth(name, kHealthy);
+                        // the old watch died with the old inode: watch the new file like a restarted healthCheck would
+                        int wd = inotify_add_watch(fd_, joinPath(dp_.devicePath, name).c_str(),
+                                                   IN_DELETE_SELF | IN_MOVE_SELF | IN_ATTRIB | IN_MODIFY);
+                        if (wd >= 0) wdToId_[wd] = name;
+                        break;
+                    }
+                continue;
+            }
+            auto it = wdToId_.find(ev->wd);
+            if (it == wdToId_.end()) continue;
+            if (ev->mask & (IN_DELETE_SELF | IN_MOVE_SELF))  // fsnotify.Remove / fsnotify.Rename (:444-448)
+                changed += setHealth(it->second, kUnhealthy);
+            if (ev->mask & IN_IGNORED) wdToId_.erase(it);   // the kernel dropped the watch (file gone)
+        }
+    }
+    return changed;
+}
+
 }  // namespace device_plugin
 
 // ----------------------------------------------------------------------------------------
@@ -371,6 +566,19 @@ int kxh_gather(const char *base_path, kxpu_devrec *out, size_t cap, size_t *n, c
     p.basePath = base_path;
     std::vector<kxpu_devrec> recs;
     device_plugin::Error e = p.gatherRecords(recs);
+    if (e) { copy_out(e.message, err, errcap); return -1; }
+    *n = recs.size();
+    if (recs.size() > cap) return -2;
+    memcpy(out, recs.data(), recs.size() * sizeof(kxpu_devrec));
+    return 0;
+}
+
+// the batched / threaded variant of the same gather
+int kxh_gather_fast(const char *base_path, unsigned threads, kxpu_devrec *out, size_t cap, size_t *n, char *err, size_t errcap) {
+    Plugin p(nullptr);
+    p.basePath = base_path;
+    std::vector<kxpu_devrec> recs;
+    device_plugin::Error e = p.gatherRecordsFast(recs, threads);
     if (e) { copy_out(e.message, err, errcap); return -1; }
     *n = recs.size();
     if (recs.size() > cap) return -2;
@@ -451,6 +659,50 @@ int kxh_allocate(void *h, const char *ids_csv, char *json, size_t cap) {
     for (size_t i = 0; i < resp.CDIDevices.size(); i++) { if (i) o += ','; jstr(o, resp.CDIDevices[i]); }
     o += "]}";
     return copy_out(o, json, cap);
+}
+
+// ---- health watcher (tests): a plugin can be added by hand so that no GPU is needed for the host logic
+int kxh_add_plugin(void *h, const char *name, const char *device_path, const char *ids_csv) {
+    Plugin *p = (Plugin *)h;
+    device_plugin::GenericDevicePlugin dp;
+    dp.devpluginName = name;
+    dp.devicePath = device_path;
+    dp.socketPath = std::string(device_plugin::kDevicePluginPath) + "kata-xpu-" + name + ".sock";
+    std::string cur;
+    for (const char *c = ids_csv;; c++) {
+        if (*c == ',' || *c == 0) {
+            if (!cur.empty()) dp.devs.push_back(device_plugin::Device{cur, device_plugin::kHealthy});
+            cur.clear();
+            if (*c == 0) break;
+        } else {
+            cur += *c;
+        }
+    }
+    p->devicePlugins.push_back(std::move(dp));
+    return (int)p->devicePlugins.size() - 1;
+}
+
+void *kxh_health_start(void *h, int plugin_index, int watch_creates, char *err, size_t errcap) {
+    Plugin *p = (Plugin *)h;
+    if (plugin_index < 0 || (size_t)plugin_index >= p->devicePlugins.size()) return nullptr;
+    auto *w = new device_plugin::HealthWatcher(p->devicePlugins[(size_t)plugin_index], watch_creates != 0);
+    device_plugin::Error e = w->start();
+    if (e) { copy_out(e.message, err, errcap); delete w; return nullptr; }
+    return w;
+}
+int kxh_health_poll(void *w, int timeout_ms) { return ((device_plugin::HealthWatcher *)w)->poll(timeout_ms); }
+void kxh_health_stop(void *w) { delete (device_plugin::HealthWatcher *)w; }
+
+// "id=Health,id=Health,..." of one plugin
+int kxh_devs(void *h, int plugin_index, char *out, size_t cap) {
+    Plugin *p = (Plugin *)h;
+    if (plugin_index < 0 || (size_t)plugin_index >= p->devicePlugins.size()) return -1;
+    std::string o;
+    for (const auto &d : p->devicePlugins[(size_t)plugin_index].devs) {
+        if (!o.empty()) o += ',';
+        o += d.ID + "=" + d.Health;
+    }
+    return copy_out(o, out, cap);
 }
 
 int kxh_list_and_watch(void *h, int plugin_index, uint8_t *out, size_t cap) {

@@ -59,6 +59,34 @@ struct Error {
     explicit operator bool() const { return failed; }
 };
 
+// healthCheck (generic_device_plugin.go:389-457) + the re-send half of ListAndWatch (:222-250) for
+// ONE plugin: an inotify watch on devicePath/<ID> of every device; Remove / Rename of the path marks
+// the device Unhealthy, Create marks it Healthy.  The reference sends one ListAndWatchResponse per
+// event; here poll() drains the whole queue, flips Health of the matching devs and reports how many
+// changed, and the caller re-encodes the list ONCE per batch (Plugin::ListAndWatchBytes): the last
+// response of a burst is byte-identical to the reference's last response.
+// watchCreates = false mirrors the reference exactly: it only adds the device paths themselves (and the
+// directory of the kubelet socket, which is out of scope here), so a Create of /dev/vfio/<group> is
+// never seen.  watchCreates = true also watches devicePath itself, which is what the code intends.
+class HealthWatcher {
+  public:
+    HealthWatcher(GenericDevicePlugin &dp, bool watchCreates = false);
+    ~HealthWatcher();
+    HealthWatcher(const HealthWatcher &) = delete;
+    HealthWatcher &operator=(const HealthWatcher &) = delete;
+    Error start();             // watcher.Add(devicePath/ID) for every dev (:421-430)
+    int poll(int timeout_ms);  // #devs whose Health changed in this batch; 0 = none; -1 = error
+    uint64_t events() const { return events_; }
+
+  private:
+    GenericDevicePlugin &dp_;
+    bool watchCreates_;
+    int fd_ = -1, dirWd_ = -1;
+    std::map<int, std::string> wdToId_;
+    uint64_t events_ = 0;
+    int setHealth(const std::string &id, const char *health);
+};
+
 class Plugin {
   public:
     // ---- seams (device_plugin.go:36-39, generic_device_plugin.go:34)
@@ -95,6 +123,9 @@ class Plugin {
 
     // raw gather only (no GPU): exposed for CPU tests of the walk
     Error gatherRecords(std::vector<kxpu_devrec> &recs);
+    // the same records, read with openat / readlinkat relative to basePath by several threads
+    // (SURVEY 8(f) row 2); falls back to gatherRecords when a seam was replaced.  threads = 0: automatic
+    Error gatherRecordsFast(std::vector<kxpu_devrec> &recs, unsigned threads = 0);
 
   private:
     kxpu_ctx *ctx_;

@@ -47,6 +47,8 @@ def host_lib():
     L = C.CDLL(HOST_LIB)
     L.kxh_gather.restype = C.c_int
     L.kxh_gather.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
+    L.kxh_gather_fast.restype = C.c_int
+    L.kxh_gather_fast.argtypes = [C.c_char_p, C.c_uint, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
     L.kxh_new.restype = C.c_void_p
     L.kxh_new.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
     L.kxh_free.argtypes = [C.c_void_p]
@@ -54,6 +56,15 @@ def host_lib():
     L.kxh_init.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t]
     L.kxh_allocate.restype = C.c_int
     L.kxh_allocate.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t]
+    L.kxh_add_plugin.restype = C.c_int
+    L.kxh_add_plugin.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
+    L.kxh_health_start.restype = C.c_void_p
+    L.kxh_health_start.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.kxh_health_poll.restype = C.c_int
+    L.kxh_health_poll.argtypes = [C.c_void_p, C.c_int]
+    L.kxh_health_stop.argtypes = [C.c_void_p]
+    L.kxh_devs.restype = C.c_int
+    L.kxh_devs.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
     L.kxh_list_and_watch.restype = C.c_int
     L.kxh_list_and_watch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     return L
@@ -65,6 +76,18 @@ def gather(base, dtype, cap=4096):
     n = C.c_size_t(0)
     err = C.create_string_buffer(512)
     rc = L.kxh_gather(base.encode(), recs.ctypes.data, cap, C.byref(n), err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return recs[:n.value]
+
+
+def gather_fast(base, dtype, threads=0, cap=4096):
+    """Same records through the batched / threaded gather."""
+    L = host_lib()
+    recs = np.zeros(cap, dtype=dtype)
+    n = C.c_size_t(0)
+    err = C.create_string_buffer(512)
+    rc = L.kxh_gather_fast(base.encode(), threads, recs.ctypes.data, cap, C.byref(n), err, 512)
     if rc != 0:
         raise RuntimeError(err.value.decode())
     return recs[:n.value]

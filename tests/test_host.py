@@ -110,3 +110,166 @@ def test_cfg1_single_gpu_golden_files(tmp_path, kx, pci_text):
     assert open(st["cdiFile"], "rb").read() == open(os.path.join(GOLDEN, "cfg1.json"), "rb").read()
     assert hp.allocate(["214"])["cdi_devices"] == ["nvidia.com/gpu=0"]
     hp.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# health events -> batched re-emit of the ListAndWatch list
+# (generic_device_plugin.go:389-457 healthCheck, :222-250 ListAndWatch)
+# ---------------------------------------------------------------------------------------------
+def _devs(L, h, idx):
+    import ctypes as C
+    buf = C.create_string_buffer(1 << 16)
+    assert L.kxh_devs(h, idx, buf, len(buf)) >= 0
+    return dict(kv.split("=") for kv in buf.value.decode().split(",") if kv)
+
+
+def test_health_watcher_marks_removed_and_renamed_groups_unhealthy(tmp_path):
+    """CPU: inotify on devicePath/<group>; Remove and Rename mark the device Unhealthy, a whole
+    burst of events is one batch; without the directory watch a re-Create is not seen (exactly
+    like the reference, which only watches the device paths and the socket directory)."""
+    import ctypes as C
+    L = fake_sysfs.host_lib()
+    vfio = tmp_path / "vfio"
+    vfio.mkdir()
+    ids = ["214", "215", "75", "76"]
+    for i in ids:
+        (vfio / i).write_text("")
+    h = L.kxh_new(None, b"/nonexistent", b"/nonexistent", b"/nonexistent")
+    idx = L.kxh_add_plugin(h, b"GH100_H100_SXM5_80GB", (str(vfio) + "/").encode(), ",".join(ids).encode())
+    err = C.create_string_buffer(512)
+    w = L.kxh_health_start(h, idx, 0, err, len(err))
+    assert w, err.value
+    try:
+        assert L.kxh_health_poll(w, 0) == 0 and set(_devs(L, h, idx).values()) == {"Healthy"}
+        os.remove(vfio / "214")
+        os.rename(vfio / "75", vfio / "75.moved")
+        os.remove(vfio / "76")
+        assert L.kxh_health_poll(w, 1000) == 3  # one batch
+        assert _devs(L, h, idx) == {"214": "Unhealthy", "215": "Healthy", "75": "Unhealthy", "76": "Unhealthy"}
+        assert L.kxh_health_poll(w, 0) == 0
+        (vfio / "214").write_text("")  # re-created: not seen without a directory watch
+        assert L.kxh_health_poll(w, 50) == 0 and _devs(L, h, idx)["214"] == "Unhealthy"
+    finally:
+        L.kxh_health_stop(w)
+        L.kxh_free(h)
+    # a device path that does not exist makes healthCheck fail (:426-429)
+    h = L.kxh_new(None, b"/nonexistent", b"/nonexistent", b"/nonexistent")
+    idx = L.kxh_add_plugin(h, b"X", (str(vfio) + "/").encode(), b"999")
+    assert not L.kxh_health_start(h, idx, 0, err, len(err)) and b"999" in err.value
+    L.kxh_free(h)
+
+
+def test_health_watcher_with_directory_watch_sees_creates(tmp_path):
+    import ctypes as C
+    L = fake_sysfs.host_lib()
+    vfio = tmp_path / "vfio"
+    vfio.mkdir()
+    for i in ("1", "2"):
+        (vfio / i).write_text("")
+    h = L.kxh_new(None, b"/nonexistent", b"/nonexistent", b"/nonexistent")
+    idx = L.kxh_add_plugin(h, b"X", str(vfio).encode(), b"1,2")
+    err = C.create_string_buffer(512)
+    w = L.kxh_health_start(h, idx, 1, err, len(err))
+    assert w, err.value
+    try:
+        os.remove(vfio / "1")
+        assert L.kxh_health_poll(w, 1000) == 1 and _devs(L, h, idx) == {"1": "Unhealthy", "2": "Healthy"}
+        (vfio / "1").write_text("")
+        (vfio / "unrelated").write_text("")
+        assert L.kxh_health_poll(w, 1000) == 1 and _devs(L, h, idx) == {"1": "Healthy", "2": "Healthy"}
+        os.remove(vfio / "1")  # the re-created file is watched again
+        assert L.kxh_health_poll(w, 1000) == 1 and _devs(L, h, idx)["1"] == "Unhealthy"
+        # flapping inside one batch: only the net change counts towards a re-emit
+        (vfio / "1").write_text("")
+        os.remove(vfio / "1")
+        (vfio / "1").write_text("")
+        L.kxh_health_poll(w, 1000)
+        assert _devs(L, h, idx)["1"] == "Healthy"
+    finally:
+        L.kxh_health_stop(w)
+        L.kxh_free(h)
+
+
+@pytest.mark.gpu
+def test_health_batch_reemits_list_and_watch_bytes(tmp_path, kx, oracle):
+    """GPU: after a batch of health events the re-encoded ListAndWatchResponse equals the oracle's
+    encoding of the same list with the same health flags (what the reference's last s.Send carries)."""
+    import ctypes as C
+    L = fake_sysfs.host_lib()
+    vfio = tmp_path / "vfio"
+    vfio.mkdir()
+    ids = [str(1000 + i) for i in range(300)]
+    for i in ids:
+        (vfio / i).write_text("")
+    h = L.kxh_new(kx.ctx, b"/nonexistent", b"/nonexistent", b"/nonexistent")
+    idx = L.kxh_add_plugin(h, b"X", str(vfio).encode(), ",".join(ids).encode())
+    err = C.create_string_buffer(512)
+    w = L.kxh_health_start(h, idx, 0, err, len(err))
+    assert w, err.value
+    try:
+        out = (C.c_uint8 * (1 << 16))()
+        n = L.kxh_list_and_watch(h, idx, out, len(out))
+        g = np.array([int(i) for i in ids], np.uint32)
+        assert bytes(out[:n]) == oracle.lw_encode(g)
+        gone = ids[3::7]
+        for i in gone:
+            os.remove(vfio / i)
+        assert L.kxh_health_poll(w, 1000) == len(gone)
+        n = L.kxh_list_and_watch(h, idx, out, len(out))
+        healthy = np.array([0 if i in set(gone) else 1 for i in ids], np.uint8)
+        assert bytes(out[:n]) == oracle.lw_encode(g, healthy)
+    finally:
+        L.kxh_health_stop(w)
+        L.kxh_free(h)
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY 8(f) row 2: batched sysfs ingestion == the reference-shaped walk, record for record
+# ---------------------------------------------------------------------------------------------
+def _synthetic_devices(n, seed):
+    rng = np.random.default_rng(seed)
+    devs = []
+    for i in range(n):
+        bdf = "%04x:%02x:%02x.%x" % (i >> 16, (i >> 8) & 0xff, (i >> 3) & 0x1f, i & 7)
+        r = rng.random()
+        d = dict(bdf=bdf, vendor=b"0x10de\n" if r < 0.6 else b"0x8086\n", device=b"0x%04x\n" % int(rng.integers(0, 0x3000)),
+                 driver="vfio-pci" if rng.random() < 0.8 else ("nvidia" if rng.random() < 0.5 else None), group=i >> 3)
+        if r > 0.97:
+            d["vendor"] = None            # unreadable vendor file
+        elif r > 0.94:
+            d["device"] = None
+        elif r > 0.92:
+            d["group"] = None
+        elif r > 0.91:
+            d["vendor"] = b"0x1\n"        # short id file
+        devs.append(d)
+    devs.append(dict(bdf="zz_real_dir", kind="dir", vendor=b"0x10de\n", device=b"0x2330\n", driver="vfio-pci", group=7))
+    devs.append(dict(bdf="zz_plain_file", kind="file"))
+    return devs
+
+
+@pytest.mark.parametrize("threads", [1, 4, 0])
+def test_fast_gather_equals_walk(tmp_path, threads):
+    from kxpu_b200.binding import DEVREC_DTYPE
+    base = fake_sysfs.make_tree(str(tmp_path / "a"), DEVICES)
+    assert fake_sysfs.gather_fast(base, DEVREC_DTYPE, threads).tobytes() == fake_sysfs.gather(base, DEVREC_DTYPE).tobytes()
+    base = fake_sysfs.make_tree(str(tmp_path / "b"), _synthetic_devices(1500, 3))
+    slow = fake_sysfs.gather(base, DEVREC_DTYPE, cap=4096)
+    fast = fake_sysfs.gather_fast(base, DEVREC_DTYPE, threads, cap=4096)
+    assert len(slow) == 1500 + 4 + 1 and fast.tobytes() == slow.tobytes()
+
+
+def test_fast_gather_error_behaviour_equals_walk(tmp_path):
+    """A non-canonical iommu_group aborts the walk at that entry (the records before it stay)."""
+    from kxpu_b200.binding import DEVREC_DTYPE
+    devs = _synthetic_devices(300, 5)
+    base = fake_sysfs.make_tree(str(tmp_path), devs)
+    victim = os.path.join(base, devs[200]["bdf"], "iommu_group")
+    if os.path.lexists(victim):
+        os.remove(victim)
+    os.symlink("/somewhere/not-a-number", victim)
+    for fn, kw in ((fake_sysfs.gather, {}), (fake_sysfs.gather_fast, dict(threads=4))):
+        with pytest.raises(RuntimeError, match="not a canonical decimal"):
+            fn(base, DEVREC_DTYPE, **kw)
+    with pytest.raises(RuntimeError):
+        fake_sysfs.gather_fast(str(tmp_path / "missing"), DEVREC_DTYPE)
