@@ -491,7 +491,7 @@ using namespace kxcomm;
 
 // every gathered candidate row / vendor row folds into the merged table with the parse rule
 __global__ void __launch_bounds__(256) merge_insert_kernel(const uint8_t *gather, int R, size_t stride, SlabCaps caps,
-                                                           KxTableDev tab) {
+                                                           KxTableDev tab, const uint32_t *peer_timeout) {
     const uint32_t per = caps.rows > caps.vendors ? caps.rows : caps.vendors;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = (int)(t / per);
@@ -500,7 +500,8 @@ __global__ void __launch_bounds__(256) merge_insert_kernel(const uint8_t *gather
     const uint8_t *slab = gather + (size_t)r * stride;
     const SlabHeader *h = reinterpret_cast<const SlabHeader *>(slab);
     if (i == 0 && h->trunc != KX_NO_OFF) atomicMin(tab.trunc, h->trunc);
-    if (i == 0 && h->overflow) tab.counters[KX_C_SLAB_OVERFLOW] = 1u;  // some rank outgrew the slab: the host retries with larger ones
+    if (i == 0 && h->overflow) atomicOr(&tab.counters[KX_C_SLAB_OVERFLOW], 1u);
+    if (t == 0 && peer_timeout && *peer_timeout) atomicOr(&tab.counters[KX_C_SLAB_OVERFLOW], 2u);  // a peer never delivered  // some rank outgrew the slab: the host retries with larger ones
     if (i < h->n_rows) {
         const SlabRow row = reinterpret_cast<const SlabRow *>(slab + slab_rows_off())[i];
         kxparse2::table_fold(tab, row.key, row.line, row.anchor);
@@ -533,7 +534,8 @@ __global__ void __launch_bounds__(256) merge_finalize_kernel(KxTableDev tab, int
 // the winning row's name stays where the all-gather put it: record its offset in the gather buffer
 __global__ void __launch_bounds__(256) merge_names_kernel(const uint8_t *gather, int R, size_t stride, SlabCaps caps,
                                                           KxTableDev tab, const int32_t *row_of_slot,
-                                                          uint32_t *row_name_off, uint32_t *row_name_len) {
+                                                          uint32_t *row_name_off, uint32_t *row_name_len, uint8_t *own_blob,
+                                                          uint32_t own_cap) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = (int)(t / caps.rows);
     const uint32_t i = (uint32_t)(t % caps.rows);
@@ -555,60 +557,82 @@ __global__ void __launch_bounds__(256) merge_names_kernel(const uint8_t *gather,
     }
     const int32_t out = row_of_slot[slot];
     if (out >= 0 && tab.min_line[slot] == row.line) {
-        row_name_off[out] = (uint32_t)((size_t)r * stride + slab_blob_off(caps) + row.name_off);
+        const size_t src = (size_t)r * stride + slab_blob_off(caps) + row.name_off;
+        if (own_blob) {
+            // the gather buffer is reused by the next load (peer-memory path): the table keeps its own copy
+            const uint32_t at = row.name_len ? atomicAdd(&tab.counters[KX_C_BLOB_CURSOR], row.name_len) : 0u;
+            if (at + row.name_len > own_cap) { tab.counters[KX_C_BLOB_OVERFLOW] = 1u; return; }
+            for (uint32_t b = 0; b < row.name_len; b++) own_blob[at + b] = gather[src + b];
+            row_name_off[out] = at;
+        } else {
+            row_name_off[out] = (uint32_t)src;
+        }
         row_name_len[out] = row.name_len;
     }
 }
 }  // namespace kxmerge
 
-int32_t kx_table_from_gather(kxpu_ctx *ctx, void *d_gather, int R, size_t stride, kxcomm::SlabCaps caps, kxpu_table **out) {
+// own_names: copy the winning names into the table's own blob and leave d_gather to the caller
+// (peer-memory path); otherwise the table takes d_gather over and serves the names from it.
+int32_t kx_table_from_gather(kxpu_ctx *ctx, void *d_gather, int R, size_t stride, kxcomm::SlabCaps caps, kxpu_table **out,
+                             bool own_names, const uint32_t *peer_timeout) {
     using namespace kxcomm;
+    auto drop_gather = [&]() { if (!own_names) cudaFreeAsync(d_gather, ctx->stream); };
     // No host round trip for the slab headers: the insert kernel flags a slab overflow of any rank
     // in the counters that are read back anyway (every rank sees the same headers and retries alike).
     cudaError_t e = cudaSuccess;
-    if ((size_t)R * stride >= 0xFFFFFFFFull) { cudaFreeAsync(d_gather, ctx->stream); return KXPU_E_UNSUPPORTED; }
+    if ((size_t)R * stride >= 0xFFFFFFFFull) { drop_gather(); return KXPU_E_UNSUPPORTED; }
     uint32_t cap = 1u << 16;
     for (int attempt = 0; attempt < 8; attempt++) {
         kxpu_table *t = nullptr;
-        int32_t rc = table_alloc(ctx, cap, 16, 1, &t);
-        if (rc != KXPU_OK) { cudaFreeAsync(d_gather, ctx->stream); return rc; }
+        const uint32_t own_cap = own_names ? (uint32_t)std::min<size_t>((size_t)R * caps.blob, 0xF0000000u) : 16u;
+        int32_t rc = table_alloc(ctx, cap, own_cap, 1, &t);
+        if (rc != KXPU_OK) { drop_gather(); return rc; }
         const uint32_t per = caps.rows > caps.vendors ? caps.rows : caps.vendors;
         const size_t nthreads = (size_t)R * per;
         kxmerge::merge_insert_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t *)d_gather, R, stride,
-                                                                                                caps, t->dev);
+                                                                                                caps, t->dev, peer_timeout);
         kxmerge::merge_finalize_kernel<<<(cap + 1 + 255) / 256, 256, 0, ctx->stream>>>(t->dev, t->row_of_slot, t->row_key, t->row_line,
                                                                                      t->row_anchor, t->row_name_off, t->row_name_len);
         kxmerge::merge_names_kernel<<<(unsigned)(((size_t)R * caps.rows + 255) / 256), 256, 0, ctx->stream>>>(
-            (const uint8_t *)d_gather, R, stride, caps, t->dev, t->row_of_slot, t->row_name_off, t->row_name_len);
+            (const uint8_t *)d_gather, R, stride, caps, t->dev, t->row_of_slot, t->row_name_off, t->row_name_len,
+            own_names ? t->blob : nullptr, own_cap);
         ctx->launches += 3;
         cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
         e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             KX_SET_ERR(ctx, "merge failed: %s", cudaGetErrorString(e));
             table_release(ctx, t);
-            cudaFreeAsync(d_gather, ctx->stream);
+            drop_gather();
             return KXPU_E_CUDA;
         }
         if (ctx->h_ctl[KX_C_SLAB_OVERFLOW]) {
+            const bool dead_peer = (ctx->h_ctl[KX_C_SLAB_OVERFLOW] & 2u) != 0;
             table_release(ctx, t);
-            cudaFreeAsync(d_gather, ctx->stream);
+            drop_gather();
+            if (dead_peer) { KX_SET_ERR(ctx, "peer-memory exchange: a rank did not deliver its slab"); return KXPU_E_NCCL; }
             return KXPU_E_CAPACITY;
         }
         if (ctx->h_ctl[KX_C_OVERFLOW] || ctx->h_ctl[KX_C_NKEYS] > t->dev.max_keys) {
             table_release(ctx, t);
-            if (cap >= (1u << 28)) { cudaFreeAsync(d_gather, ctx->stream); return KXPU_E_UNSUPPORTED; }
+            if (cap >= (1u << 28)) { drop_gather(); return KXPU_E_UNSUPPORTED; }
             cap <<= 2;
             continue;
         }
         t->n_rows = ctx->h_ctl[KX_C_NROWS];
-        t->gather = d_gather;               // names are served from the gathered slabs
-        t->blob = (uint8_t *)d_gather;
-        t->blob_cap = (uint32_t)((size_t)R * stride);
+        if (own_names) {
+            if (ctx->h_ctl[KX_C_BLOB_OVERFLOW]) { table_release(ctx, t); return KXPU_E_UNSUPPORTED; }
+            t->blob_used = ctx->h_ctl[KX_C_BLOB_CURSOR];
+        } else {
+            t->gather = d_gather;               // names are served from the gathered slabs
+            t->blob = (uint8_t *)d_gather;
+            t->blob_cap = (uint32_t)((size_t)R * stride);
+        }
         *out = t;
         return KXPU_OK;
     }
-    cudaFreeAsync(d_gather, ctx->stream);
-    return KXPU_E_CAPACITY;
+    drop_gather();
+    return KXPU_E_UNSUPPORTED;
 }
 
 void kx_table_local_view(kxpu_table *t, KxTableDev *dev, uint32_t *cap, uint32_t *n_rows, uint32_t *blob_used,

@@ -25,7 +25,7 @@ struct kxpu_table;
 int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned long long base,
                        unsigned long long carry_in, int check_valid, kxpu_table **out);
 int32_t kx_table_from_gather(kxpu_ctx *ctx, void *d_gather, int nranks, size_t slab_stride, kxcomm::SlabCaps caps,
-                             kxpu_table **out);
+                             kxpu_table **out, bool own_names, const uint32_t *peer_timeout);
 void kx_table_local_view(kxpu_table *t, KxTableDev *dev, uint32_t *cap, uint32_t *n_rows, uint32_t *blob_used,
                          const uint32_t **row_key, const unsigned long long **row_line, const unsigned long long **row_anchor,
                          const uint32_t **row_name_off, const uint32_t **row_name_len, const uint8_t **blob);
@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(256) pack_vendors_kernel(uint8_t *slab, SlabCa
 
 }  // namespace kxcomm
 
+#include "p2p.cuh"
+
 using namespace kxcomm;
 
 extern "C" int32_t kxpu_comm_unique_id(uint8_t id_out[KXPU_COMM_ID_BYTES]) {
@@ -134,6 +136,9 @@ extern "C" int32_t kxpu_comm_init(kxpu_ctx *ctx, int32_t nranks, int32_t rank, c
     ctx->nccl_comm = comm;
     ctx->nranks = nranks;
     ctx->rank = rank;
+    p2p_setup(ctx, [&](const void *src, void *dst, size_t nbytes) {
+        return g_nccl.all_gather(src, dst, nbytes, /*ncclUint8*/ 1, ctx->nccl_comm, ctx->stream);
+    });
     return KXPU_OK;
 }
 
@@ -143,6 +148,7 @@ extern "C" int32_t kxpu_comm_destroy(kxpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->nccl_comm) {
         cudaStreamSynchronize(ctx->stream);
+        p2p_teardown(ctx);
         g_nccl.comm_destroy(ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
         ctx->nranks = 1;
@@ -172,7 +178,60 @@ extern "C" int32_t kxpu_pciids_load_sharded(kxpu_ctx *ctx, const void *d_text_sh
     kx_table_local_view(local, &dev, &cap, &n_rows, &blob_used, &row_key, &row_line, &row_anchor, &row_name_off,
                         &row_name_len, &blob);
 
+    // ---- peer-memory path: pack into my slot, push it to every peer, wait for everybody's flag, merge
+    if (ctx->p2p_ok) {
+        const SlabCaps caps = kDefaultCaps;
+        const uint32_t e = ++ctx->p2p_epoch;
+        const int b = (int)(e & 1u);
+        const size_t slot0 = P2P_FLAGS_BYTES + (size_t)b * (size_t)R * ctx->p2p_stride;
+        if (ctx->stage_timing) cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE], ctx->stream);
+        static const bool ptrace = getenv("KXPU_TRACE_MERGE") != nullptr;
+        static cudaEvent_t pev[4];
+        static bool pev_ok = false;
+        if (ptrace && !pev_ok) { for (auto &e2 : pev) cudaEventCreate(&e2); pev_ok = true; }
+        if (ptrace) cudaEventRecord(pev[0], ctx->stream);
+        PushParams PP;
+        memset(&PP, 0, sizeof PP);
+        PP.nranks = R; PP.epoch = e; PP.caps = caps; PP.scratch = ctx->p2p_scratch;
+        PP.n_rows = n_rows; PP.blob_used = blob_used; PP.row_key = row_key; PP.row_name_off = row_name_off;
+        PP.row_name_len = row_name_len; PP.row_line = row_line; PP.row_anchor = row_anchor; PP.trunc = dev.trunc;
+        PP.vendor_first = dev.vendor_first; PP.blob = blob;
+        for (int q = 0; q < R; q++) {
+            PP.dst[q] = ctx->p2p_peer[q] + slot0 + (size_t)ctx->rank * ctx->p2p_stride;
+            PP.flag[q] = reinterpret_cast<uint32_t *>(ctx->p2p_peer[q]) + b * kxpu_ctx::KX_P2P_MAX_RANKS + ctx->rank;
+        }
+        pack_push_kernel<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(PP);
+        if (ptrace) cudaEventRecord(pev[1], ctx->stream);
+        wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(ctx->p2p_local) + b * kxpu_ctx::KX_P2P_MAX_RANKS,
+                                                     R, e, ctx->p2p_scratch + 1);
+        ctx->launches += 2;
+        if (ptrace) cudaEventRecord(pev[2], ctx->stream);
+        kxpu_table *merged = nullptr;
+        rc = kx_table_from_gather(ctx, ctx->p2p_local + slot0, R, ctx->p2p_stride, caps, &merged, /*own_names=*/true, ctx->p2p_scratch + 1);
+        if (ptrace) {
+            cudaEventRecord(pev[3], ctx->stream);
+            cudaEventSynchronize(pev[3]);
+            float a = 0, b2 = 0, c2 = 0;
+            cudaEventElapsedTime(&a, pev[0], pev[1]); cudaEventElapsedTime(&b2, pev[1], pev[2]); cudaEventElapsedTime(&c2, pev[2], pev[3]);
+            static int calls = 0;
+            if (++calls % 8 == 0) fprintf(stderr, "[kxpu merge trace] pack+push %.1f us  wait %.1f us  merge+sync %.1f us  (peer memory, %d ranks)\n", a * 1e3, b2 * 1e3, c2 * 1e3, R);
+        }
+        if (ctx->stage_timing) { cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE + 1], ctx->stream); ctx->ev_used[KXPU_T_MERGE] = true; }
+        if (rc == KXPU_E_NCCL) {  // a peer never delivered (flagged by the wait kernel, seen by the merge)
+            cudaMemsetAsync(ctx->p2p_scratch, 0, 256, ctx->stream);
+            kx_table_release(ctx, local);
+            return rc;
+        }
+        if (rc != KXPU_E_CAPACITY) {  // a slab outgrew the fixed exchange region: every rank falls back to NCCL below
+            kx_table_release(ctx, local);
+            if (rc != KXPU_OK) return rc;
+            *out = merged;
+            return KXPU_OK;
+        }
+    }
+
     SlabCaps caps{32768u, 8192u, 1u << 20};
+    if (ctx->p2p_ok) { caps.rows *= 4; caps.vendors = 65536; caps.blob *= 8; }  // the default capacities just overflowed
     for (int attempt = 0; attempt < 6; attempt++) {
         const size_t sb = (slab_bytes(caps) + 255) / 256 * 256;
         uint8_t *d_slab = nullptr, *d_gather = nullptr;
@@ -211,7 +270,7 @@ extern "C" int32_t kxpu_pciids_load_sharded(kxpu_ctx *ctx, const void *d_text_sh
         cudaFreeAsync(d_slab, ctx->stream);
         // 4. min-merge into a fresh table (keeps d_gather: the names live there)
         kxpu_table *merged = nullptr;
-        rc = kx_table_from_gather(ctx, d_gather, R, sb, caps, &merged);
+        rc = kx_table_from_gather(ctx, d_gather, R, sb, caps, &merged, /*own_names=*/false, nullptr);
         if (ctx->stage_timing) { cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE + 1], ctx->stream); ctx->ev_used[KXPU_T_MERGE] = true; }
         if (trace) {
             cudaEventRecord(tev[3], ctx->stream);

@@ -26,6 +26,15 @@ struct kxpu_ctx {
     // NCCL (lazy)
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    // peer-memory exchange of the sharded load (comm.cu): this rank's region and the peers' regions
+    // mapped through CUDA IPC; layout [flags u32[2][16] | pad to 256 | slab[2][nranks]]
+    static constexpr int KX_P2P_MAX_RANKS = 16;
+    uint8_t *p2p_local = nullptr;
+    uint8_t *p2p_peer[KX_P2P_MAX_RANKS] = {};
+    size_t p2p_stride = 0;
+    uint32_t p2p_epoch = 0;
+    uint32_t *p2p_scratch = nullptr;  // device: [0] push-done counter, [1] wait timeout flag
+    bool p2p_ok = false;
     int parse_version = 2;
 };
 
