@@ -3,8 +3,9 @@
 
 Workload (config.workload): BASELINE.json configs[3] -- utils/pci.ids replicated x1000
 (1 458 186 000 B of text per GPU) + a 2^20-key (vendor,device) join, first occurrence wins.
-One step = parse the text into the (vendor,device) table (parse + finalize kernels, plus the
-NCCL all-gather/merge of hit rows when N > 1) and join 2^20 keys against it.
+One step = parse the text into the (vendor,device) table (parse + resolve + finalize kernels, plus
+the exchange/merge of candidate rows over NVSwitch peer memory when N > 1) and join 2^20 keys
+against it (N = 1: one kxpu_pciids_join_device call).
 
   value      text bytes consumed per second by the whole job, inputs resident in HBM,
              device-timed (CUDA events on the library's stream), max over ranks.
@@ -12,8 +13,9 @@ NCCL all-gather/merge of hit rows when N > 1) and join 2^20 keys against it.
              pinned host text -> H2D, kernels, D2H of the row handles, every step.
   roofline   parse kernel: text bytes / mean kernel time vs the measured HBM copy bandwidth.
   N > 1      weak scaling: every rank holds its own x1000 shard of one logical x(1000*N) text
-             (shards cut at copy boundaries = vendor-line boundaries), hit rows exchanged with
-             one ncclAllGather; torch.distributed is only used for the rendezvous/barrier.
+             (shards cut at copy boundaries = vendor-line boundaries), candidate rows pushed into
+             every peer's memory over NVLink (ncclAllGather as fallback); torch.distributed is
+             only used for the rendezvous/barrier.
   --impl reference   the reference's own algorithm (getDeviceName: one linear rescan of the
              text per key, pkg/device_plugin/device_plugin.go:208-275) restated in C
              (oracle/, Go toolchain absent), all host threads, bounded sample per step.
