@@ -2,20 +2,25 @@
 """bench.py -- BASELINE.json metric "pci.ids parse GB/s; device lookups/sec" on B200.
 
 Workload (config.workload): BASELINE.json configs[3] -- utils/pci.ids replicated x1000
-(1 458 186 000 B of text per GPU) + a 2^20-key (vendor,device) join, first occurrence wins.
-One step = parse the text into the (vendor,device) table (parse + resolve + finalize kernels, plus
-the exchange/merge of candidate rows over NVSwitch peer memory when N > 1) and join 2^20 keys
-against it (N = 1: one kxpu_pciids_join_device call).
+(1 458 186 000 B of text) + a 2^20-key (vendor,device) join, first occurrence wins.
+One step = parse the text into the (vendor,device) table and join the 2^20 keys against it:
+  N = 1   one kxpu_pciids_join_device call (parse + resolve + finalize + join, one host round trip);
+  N > 1   STRONG scaling (default): the SAME 1.458 GB text is cut into N shards at vendor lines
+          (kxpu_plan_shards), the SAME 2^20 keys into N slices; one kxpu_pciids_join_sharded call per
+          step: parse the shard, all-reduce(min) of the first anchors and push of the winning rows over
+          NVSwitch peer memory, insert, probe the key slice with the hits stored into every rank.
+          A WEAK-scaling measurement (every rank its own x1000 shard of one logical x(1000*N) text and
+          its own 2^20 keys) rides in the same line under "weak_scaling" (--scaling weak makes it the
+          headline instead).
 
   value      text bytes consumed per second by the whole job, inputs resident in HBM,
              device-timed (CUDA events on the library's stream), max over ranks.
-  e2e        same metric through the host-buffer C-ABI calls (kxpu_pciids_load + kxpu_lookup):
-             pinned host text -> H2D, kernels, D2H of the row handles, every step.
+  e2e        same metric through the host side: pinned host text -> H2D, kernels, D2H of the row
+             handles, every step (N = 1: kxpu_pciids_load + kxpu_lookup on host buffers).
   roofline   parse kernel: text bytes / mean kernel time vs the measured HBM copy bandwidth.
-  N > 1      weak scaling: every rank holds its own x1000 shard of one logical x(1000*N) text
-             (shards cut at copy boundaries = vendor-line boundaries), candidate rows pushed into
-             every peer's memory over NVLink (ncclAllGather as fallback); torch.distributed is
-             only used for the rendezvous/barrier.
+  parity     outside the timed region every rank's table and join result are compared with the
+             oracle's table of the whole text (kxo_table_build on the 1.458 GB buffer, rank 0) and
+             with each other ("parity_checked").
   --impl reference   the reference's own algorithm (getDeviceName: one linear rescan of the
              text per key, pkg/device_plugin/device_plugin.go:208-275) restated in C
              (oracle/, Go toolchain absent), all host threads, bounded sample per step.
@@ -38,6 +43,13 @@ NQ = 1 << 20
 METRIC = "pci.ids parse GB/s (x1000 text + 2^20-key join); device lookups/s reported beside it"
 
 
+def workload_config(n_text):
+    """Identical in both arms (ours / reference) and for every N: the job is the same job."""
+    return {"workload": "cfg4: pci.ids x1000 (1 458 186 000 B) + 2^20-key join, first occurrence wins",
+            "text_bytes": int(n_text), "keys": NQ,
+            "l2": "input (1.458 GB) larger than L2 (126 MB); no flush needed"}
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -46,10 +58,10 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per parse launch from the committed ncu capture, if any."""
+def ncu_traffic(name="parse_kernel_traffic.json"):
+    """dram bytes per launch of a kernel from the committed ncu capture, if any."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "parse_kernel_traffic.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
         return d.get("dram_bytes_per_launch")
     except Exception:
         return None
@@ -99,7 +111,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "window": "warm-up + timed region, 100 ms period"}
+                "samples": len(sm), "window": "warm-up + settle steps + timed region, 100 ms period"}
 
 
 def host_threads():
@@ -107,6 +119,32 @@ def host_threads():
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node its GPU hangs
+    off: without it 8 ranks pin 1.46 GB each on whatever node the launcher started them on and half
+    of the H2D traffic crosses the socket link.  Returns a short description for the JSON line."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if len(bus) > 12 and bus.startswith("0000"):
+            bus = bus[4:]  # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return "numa_node -1 (single node)"
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return "node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:  # noqa: BLE001
+        return "unbound (%s)" % type(e).__name__
 
 
 def reference_sample(text_x, present_keys, n_keys, threads, seed):
@@ -142,10 +180,10 @@ def run_reference(args, rank, out_fd):
     gbs = len(text) * COPIES / job_s / 1e9  # same meaning as the GPU arm's value: job text bytes / job time
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "cfg4: pci.ids x1000 (1 458 186 000 B) + 2^20-key join, first occurrence wins",
-                   "text_bytes": len(text) * COPIES, "keys": NQ, "sample_keys_per_step": n_keys},
+        "config": workload_config(len(text) * COPIES),
+        "sample_keys_per_step": n_keys,
         "lookups_per_s": tot_k / tot_t,
         "scan_gbs": scan_gbs,  # text bytes the scanners consumed per second (the reference re-reads the text per key)
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "scan_gbs": scan_gbs,
@@ -162,6 +200,16 @@ def emit_line(fd, obj):
     os.write(fd, (json.dumps(obj) + "\n").encode())
 
 
+def expected_lines(orows, q):
+    """line offset the oracle's table gives for every key (-1 = miss)."""
+    order = np.argsort(orows["key"])
+    sk = orows["key"][order]
+    pos = np.searchsorted(sk, q)
+    pos[pos >= len(sk)] = 0
+    hit = sk[pos] == q
+    return np.where(hit, orows["line_off"][order][pos].astype(np.int64), -1)
+
+
 def main():
     # Libraries (NCCL's version banner, for one) print to stdout; the contract is ONE JSON line on
     # stdout, so everything else is sent to stderr and the line is written to the saved descriptor.
@@ -173,9 +221,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="headline measurement at N > 1")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--settle-steps", type=int, default=1200, help="untimed extra warm-up steps (clock settling)")
+    ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--settle-ms", type=float, default=400.0,
+                    help="untimed extra warm-up (clock settling + nvidia-smi samples); the step count is reported in the line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -188,7 +239,9 @@ def main():
 
     import kxpu_b200 as K
     from kxpu_b200 import workloads as W
+    B = K.binding
 
+    numa = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch
@@ -200,39 +253,18 @@ def main():
     text = W.load_pci_ids()
     n1 = len(text)
     n = n1 * COPIES
-    d_one = kx.dev_alloc(n1)
-    kx.upload(d_one, np.frombuffer(text, np.uint8))
-    d_text = kx.dev_alloc(n)
-    kx.replicate(d_text, d_one, n1, COPIES)
 
-    if world > 1:
+    # the whole logical text in pinned host memory (source of the e2e copies and of the shard plan)
+    h_text, h_ptr = kx.pinned(n)
+    h_text.reshape(COPIES, n1)[:] = np.frombuffer(text, np.uint8)
+
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
         import torch
-        uid = torch.zeros(K.binding.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.from_numpy(kx.comm_unique_id()))
-        dist.broadcast(uid, 0)
-        kx.comm_init(world, rank, uid.cpu().numpy())
-
-    def load():
-        if world > 1:
-            return kx.pciids_load_sharded(d_text, n, rank * n)
-        return kx.pciids_load_device(d_text, n)
-
-    # present keys (for the query mix) come from the product's own table
-    tab = load()
-    present, _, _ = kx.table_export(tab)
-    tab.free()
-    keys = W.make_queries(present, NQ, 2 + rank)
-    d_keys = kx.dev_alloc(NQ * 4)
-    d_rows = kx.dev_alloc(NQ * 4)
-    kx.upload(d_keys, keys)
-
-    def step():
-        if world == 1:  # parse + join in one call: no host round trip between the two
-            return kx.pciids_join_device(d_text, n, d_keys, NQ, d_rows)
-        t = load()
-        kx.lookup_device(t, d_keys, NQ, d_rows)
-        return t
+        v = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
 
     def barrier():
         kx.sync()
@@ -241,154 +273,244 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # clocks are sampled from before the warm-up to the end of the timed region (the timed region
-    # alone, K x ~1 ms, is shorter than nvidia-smi's sampling period)
+    if world > 1:
+        import torch
+        uid = torch.zeros(B.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.from_numpy(kx.comm_unique_id()))
+        dist.broadcast(uid, 0)
+        kx.comm_init(world, rank, uid.cpu().numpy())
+
+    # present keys (for the query mix): the same on every rank, from the product's own table of one copy
+    t1 = kx.pciids_load(np.frombuffer(text, np.uint8))
+    present, _, _ = kx.table_export(t1)
+    t1.free()
+    keys = W.make_queries(present, NQ, 2)  # ONE logical key array (cfg4, seed 2)
+
+    # ---------------------------------------------------------------- workloads
+    def make_strong():
+        """The same 1.458 GB text cut into `world` shards, the same keys into `world` slices."""
+        a, b = K.plan_shards(h_text, world)[rank]
+        per = NQ // world
+        lo, hi = rank * per, (rank + 1) * per if rank + 1 < world else NQ
+        d_text = kx.dev_alloc(max(b - a, 16))
+        kx.upload(d_text, h_text[a:b])
+        d_keys = kx.dev_alloc((hi - lo) * 4)
+        kx.upload(d_keys, keys[lo:hi])
+        d_rows = kx.dev_alloc(NQ * 4)
+        w = dict(kind="strong", d_text=d_text, n=b - a, base=a, d_keys=d_keys, nq=hi - lo, key_off=lo, d_rows=d_rows,
+                 h_src=h_text[a:b], h_keys=keys[lo:hi], job_bytes=n, h_rows=np.empty(NQ, np.int32))
+        if world == 1:
+            w["step"] = lambda: kx.pciids_join_device(d_text, n, d_keys, NQ, d_rows)
+        else:
+            w["step"] = lambda: kx.pciids_join_sharded(d_text, b - a, a, d_keys, hi - lo, lo, NQ, d_rows)
+        w["load"] = (lambda: kx.pciids_load_device(d_text, n)) if world == 1 else (lambda: kx.pciids_load_sharded(d_text, b - a, a))
+        return w
+
+    def make_weak():
+        """Every rank its own x1000 shard of one logical x(1000*world) text and its own 2^20 keys."""
+        d_text = kx.dev_alloc(n)
+        kx.upload(d_text, h_text)
+        my_keys = W.make_queries(present, NQ, 2 + rank)
+        d_keys = kx.dev_alloc(NQ * 4)
+        kx.upload(d_keys, my_keys)
+        d_rows = kx.dev_alloc(NQ * 4)
+
+        def step():
+            t = kx.pciids_load_sharded(d_text, n, rank * n)
+            kx.lookup_device(t, d_keys, NQ, d_rows)
+            return t
+        return dict(kind="weak", d_text=d_text, n=n, base=rank * n, d_keys=d_keys, nq=NQ, key_off=0, d_rows=d_rows,
+                    h_src=h_text, h_keys=my_keys, job_bytes=world * n, step=step, h_rows=np.empty(NQ, np.int32),
+                    load=lambda: kx.pciids_load_sharded(d_text, n, rank * n))
+
+    def free_workload(w):
+        for k in ("d_text", "d_keys", "d_rows"):
+            kx.dev_free(w[k])
+
+    def measure(w, steps, warmup, settle_ms, sampler=None):
+        """Device-timed K steps (max over ranks) + per-kernel device times from separate passes."""
+        for _ in range(warmup):
+            w["step"]().free()
+        kx.sync()
+        t0 = time.time()
+        w["step"]().free()
+        kx.sync()
+        one = max(time.time() - t0, 1e-5)
+        settle = int(max_over_ranks(min(settle_ms * 1e-3 / one, 5000)))  # same count on all ranks
+        for _ in range(settle):
+            w["step"]().free()
+        barrier()
+        launches0 = kx.launch_count()
+        kx.set_stage_timing(False)  # the per-stage events are for the separate per-kernel passes below
+        kx.timer_begin()
+        t_wall = time.time()
+        for _ in range(steps):
+            w["step"]().free()
+        ms_total = kx.timer_end()
+        kx.set_stage_timing(True)
+        barrier()
+        wall_ms = (time.time() - t_wall) * 1e3
+        launches = kx.launch_count() - launches0
+        clocks = sampler.stop() if sampler is not None else None
+        km = {k: [] for k in ("parse", "parse_resolve", "finalize", "merge", "lookup")}
+        for _ in range(min(steps, 10)):
+            t = w["step"]()
+            tm = kx.timings()
+            km["parse"].append(tm[B.T_PARSE]); km["parse_resolve"].append(tm[B.T_RESOLVE]); km["finalize"].append(tm[B.T_FINALIZE])
+            km["merge"].append(tm[B.T_MERGE]); km["lookup"].append(tm[B.T_LOOKUP])
+            t.free()
+        ms_step = max_over_ranks(ms_total) / steps
+        return dict(ms_per_step=ms_step, value=w["job_bytes"] / (ms_step * 1e-3) / 1e9, wall_ms_per_step=wall_ms / steps,
+                    launches=int(launches), settle_steps=settle, clocks=clocks,
+                    kernel_ms={k: float(np.mean(v)) for k, v in km.items()})
+
+    def measure_e2e(w, steps):
+        """The same step from HOST buffers: pinned text (shard) -> H2D, kernels, D2H of the row handles."""
+        ms = []
+        for i in range(1 + steps):
+            barrier()
+            t0 = time.time()
+            if world == 1:
+                t = kx.pciids_load(w["h_src"])
+                rows = kx.lookup(t, w["h_keys"])
+            else:
+                kx.upload(w["d_text"], w["h_src"])
+                kx.upload(w["d_keys"], w["h_keys"])
+                t = w["step"]()
+                rows = kx.download(w["d_rows"], NQ * 4, np.int32)
+            barrier()
+            if i > 0:
+                ms.append((time.time() - t0) * 1e3)
+            t.free()
+        e2e_step = max_over_ranks(float(np.mean(ms)))
+        h2d = int(len(w["h_src"]) + 4 * len(w["h_keys"]))
+        return dict(value=w["job_bytes"] / (e2e_step * 1e-3) / 1e9, unit="GB/s", h2d_bytes_per_step=h2d,
+                    d2h_bytes_per_step=int(4 * NQ), ms_per_step=e2e_step, rows=rows)
+
+    def check_parity(w):
+        """Every rank: table hash + join result vs the oracle's table of the WHOLE text (rank 0 builds it
+        with kxo_table_build on the 1.458 GB buffer, outside every timed region)."""
+        t = w["step"]()
+        tk, to, tr = kx.table_export(t)
+        got = kx.download(w["d_rows"], NQ * 4, np.int32)
+        line_of_row = np.full(t.rows + 1, -1, np.int64)
+        line_of_row[tr] = to.astype(np.int64)
+        got_line = np.where(got >= 0, line_of_row[np.maximum(got, 0)], -1)
+        t.free()
+        ok, detail = True, {}
+        if w["kind"] == "strong":
+            if rank == 0:
+                from oracle import oracle as O
+                O.build()
+                t0 = time.time()
+                orows = O.table_build(h_text)
+                detail["oracle_s"] = time.time() - t0
+                ok = bool(np.array_equal(tk, orows["key"]) and np.array_equal(to, orows["line_off"]))
+                ok = ok and bool(np.array_equal(got_line, expected_lines(orows, keys)))
+                detail["rows"] = int(len(orows)); detail["hits"] = int((got >= 0).sum())
+        else:  # weak: the logical text is x(1000*world); first occurrence wins -> the single-copy table; own keys
+            from oracle import oracle as O
+            O.build()
+            orows = O.table_build(text)
+            ok = bool(np.array_equal(tk, orows["key"]) and np.array_equal(to, orows["line_off"]))
+            ok = ok and bool(np.array_equal(got_line, expected_lines(orows, w["h_keys"])))
+        if dist is not None:
+            import torch
+            hv = int(np.bitwise_xor.reduce(tk.astype(np.uint64) * np.uint64(31) + to)) & 0x7FFFFFFFFFFFFFFF
+            if w["kind"] == "strong":
+                hv ^= int(np.bitwise_xor.reduce(got.astype(np.int64).view(np.uint64) * np.arange(1, NQ + 1, dtype=np.uint64))) & 0x7FFFFFFFFFFFFFFF
+            h = torch.tensor([hv, 1 if ok else 0], dtype=torch.int64, device="cuda")
+            hs = [torch.zeros_like(h) for _ in range(world)]
+            dist.all_gather(hs, h)
+            ok = all(int(x[0].item()) == int(hs[0][0].item()) for x in hs) and all(int(x[1].item()) == 1 for x in hs)
+            detail["identical_on_all_ranks"] = all(int(x[0].item()) == int(hs[0][0].item()) for x in hs)
+        return ok, detail
+
+    # ---------------------------------------------------------------- headline + second measurement
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        step().free()
-    for _ in range(args.settle_steps):  # ~0.5 s of untimed steps: clocks settle and nvidia-smi gets samples (same count on all ranks)
-        step().free()
-    parse_ms, fin_ms, merge_ms, look_ms, res_ms = [], [], [], [], []
-    barrier()
-    launches0 = kx.launch_count()
-    kx.set_stage_timing(False)  # the per-stage events are for the separate per-kernel passes below
-    kx.timer_begin()
-    t_wall = time.time()
-    tabs = []
-    for _ in range(args.steps):
-        t = step()
-        tabs.append(t)
+    modes = [args.scaling] + ([("weak" if args.scaling == "strong" else "strong")] if world > 1 else [])
+    results = {}
+    for i, mode in enumerate(modes):
+        w = make_strong() if mode == "strong" else make_weak()
+        r = measure(w, args.steps, args.warmup, args.settle_ms, sampler if (i == 0 and rank == 0) else None)
+        r["e2e"] = measure_e2e(w, args.e2e_steps)
+        r["e2e"].pop("rows")
+        ok, detail = check_parity(w)
+        r["parity_checked"], r["parity"] = ok, detail
+        # the join alone (kernel time, and through the host-buffer ABI)
+        t = w["load"]()
+        look, lk_ms = [], []
+        for j in range(6):
+            kx.lookup_device(t, w["d_keys"], w["nq"], w["d_rows"])
+            look.append(kx.timings()[B.T_LOOKUP])
+            barrier()
+            t0 = time.time()
+            kx.lookup(t, w["h_keys"])
+            if j > 0:
+                lk_ms.append((time.time() - t0) * 1e3)
         t.free()
-    ms_total = kx.timer_end()
-    kx.set_stage_timing(True)
-    barrier()
-    wall_ms = (time.time() - t_wall) * 1e3
-    launches = kx.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-
-    # per-kernel device times (separate, untimed passes so event queries do not perturb the run)
-    for _ in range(min(args.steps, 10)):
-        t = load()
-        tm = kx.timings()
-        parse_ms.append(tm[K.binding.T_PARSE]); fin_ms.append(tm[K.binding.T_FINALIZE]); merge_ms.append(tm[K.binding.T_MERGE])
-        res_ms.append(tm[K.binding.T_RESOLVE])
-        kx.lookup_device(t, d_keys, NQ, d_rows)
-        look_ms.append(kx.timings()[K.binding.T_LOOKUP])
-        t.free()
-
-    if dist is not None:
-        import torch
-        v = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        ms_total = float(v.item())
-    ms_step = ms_total / args.steps
-    value = world * n / (ms_step * 1e-3) / 1e9
-
-    # e2e through the host-buffer ABI: pinned host text, H2D + kernels + D2H per step
-    h_text, h_ptr = kx.pinned(n)
-    h_text.reshape(COPIES, n1)[:] = np.frombuffer(text, np.uint8)
-    e2e_ms = []
-    for i in range(1 + args.e2e_steps):
-        barrier()
-        t0 = time.time()
-        if world > 1:
-            kx.upload(d_text, h_text)
-            t = load()
+        r["lookup_kernel_ms"], r["lookup_host_ms"], r["nq_rank"] = float(np.mean(look[1:])), float(np.mean(lk_ms)), w["nq"]
+        r["shard_bytes"] = int(w["n"])
+        results[mode] = r
+        if i + 1 < len(modes) or world > 1:
+            free_workload(w)
         else:
-            t = kx.pciids_load(h_text)
-        rows = kx.lookup(t, keys)
-        barrier()
-        if i > 0:
-            e2e_ms.append((time.time() - t0) * 1e3)
-        t.free()
-    # the join alone through the host-buffer ABI (H2D keys, kernel, D2H row handles)
-    lk_ms = []
-    t = load()
-    for i in range(6):
-        barrier()
-        t0 = time.time()
-        rows = kx.lookup(t, keys)
-        if i > 0:
-            lk_ms.append((time.time() - t0) * 1e3)
-    t.free()
-    e2e_step = float(np.mean(e2e_ms))
-    if dist is not None:
-        import torch
-        v = torch.tensor([e2e_step], dtype=torch.float64, device="cuda")
-        dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        e2e_step = float(v.item())
-    e2e_val = world * n / (e2e_step * 1e-3) / 1e9
+            results["_w"] = w
+    head = results[args.scaling]
 
     line = None
     if rank == 0:
         peak, peak_src = measured_peak()
-        pk = float(np.mean(parse_ms))
-        achieved = n / (pk * 1e-3) / 1e9
+        pk = head["kernel_ms"]["parse"]
+        shard_bytes = head["shard_bytes"]
+        achieved = shard_bytes / (pk * 1e-3) / 1e9
+        km = dict(head["kernel_ms"])
+        stages = {k: v for k, v in km.items()}
+        limiting = max(stages, key=lambda k: stages[k])
         line = {
-            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "cfg4: pci.ids x1000 (1 458 186 000 B per GPU) + 2^20-key join, first occurrence wins",
-                       "text_bytes_per_gpu": n, "keys_per_gpu": NQ, "parallelism": "shard-by-vendor-range x%d" % world,
-                       "l2": "input (1.458 GB) larger than L2 (126 MB); no flush needed"},
-            "lookups_per_s": world * NQ / (float(np.mean(look_ms)) * 1e-3),
-            "lookups_per_s_e2e": world * NQ / (float(np.mean(lk_ms)) * 1e-3),
-            "kernel_ms": {"parse": pk, "parse_resolve": float(np.mean(res_ms)), "finalize": float(np.mean(fin_ms)), "merge": float(np.mean(merge_ms)),
-                          "lookup": float(np.mean(look_ms))},
-            "wall_ms_per_step": wall_ms / args.steps,
+            "metric": METRIC, "value": head["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "settle_steps": head["settle_steps"], "ms_per_step": head["ms_per_step"],
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(n),
+            "parallelism": ("1 GPU" if world == 1 else
+                            "%s: text cut at vendor lines into %d shards, keys into %d slices; peer-memory exchange over NVSwitch"
+                            % (args.scaling, world, world)),
+            "shard_bytes_rank0": shard_bytes,
+            "lookups_per_s": world * head["nq_rank"] / (head["lookup_kernel_ms"] * 1e-3),
+            "lookups_per_s_e2e": world * head["nq_rank"] / (head["lookup_host_ms"] * 1e-3),
+            "lookups_note": "kernel alone on rank 0's slice; keys + rows (8 B/key) are L2 resident after the first pass, "
+                            "the table (2.6 MB) always is: a throughput figure, not an HBM roofline",
+            "kernel_ms": km, "limiting_stage": limiting,
+            "kernel_ms_note": "device time per stage on rank 0 from separate passes with per-stage CUDA events; "
+                              "merge = phase A push .. insert of the winners (includes waiting for the slowest rank)",
+            "wall_ms_per_step": head["wall_ms_per_step"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "kxparse5::parse_kernel_v5",
-                         "algorithmic_bytes_per_launch": n},
-            "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(n + 4 * NQ),
-                    "d2h_bytes_per_step": int(4 * NQ), "ms_per_step": e2e_step},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+                         "traffic": ncu_traffic() if world == 1 else None, "peak_source": peak_src,
+                         "kernel": "kxparse5::parse_kernel_v5", "algorithmic_bytes_per_launch": shard_bytes},
+            "e2e": dict(head["e2e"], numa=numa,
+                        note="PCIe bound: every rank copies its shard from pinned host memory each step "
+                             "(Gen5 x16 ~ 55-57 GB/s per GPU in practice, ~64 GB/s nominal)"),
+            "parity_checked": bool(head["parity_checked"]), "parity": head["parity"],
+            "gpu_launches": head["launches"],
+            "clocks": head["clocks"],
         }
-        if world == 1:
-            # the other rows of the hot path, through the host-buffer ABI,
-            # device time of their kernels from the library's CUDA events; not part of `value`
-            recs = W.cfg3_records(present)
-            devs = W.cfg5_devices()
-            cls_ms, emit_j_ms, emit_y_ms = [], [], []
-            for _ in range(4):
-                res = kx.classify(recs)
-                cls_ms.append(kx.timings()[K.binding.T_CLASSIFY])
-                j = kx.cdi_emit(K.binding.FMT_JSON, devs)
-                emit_j_ms.append(kx.timings()[K.binding.T_EMIT])
-                y = kx.cdi_emit(K.binding.FMT_YAML, devs)
-                emit_y_ms.append(kx.timings()[K.binding.T_EMIT])
-            # configs[1] (cfg2): the real utils/pci.ids once + 1024 lookups -- latency, not bandwidth
-            one = np.frombuffer(text, np.uint8)
-            q2 = W.cfg2_queries(present)
-            c2_dev, c2_e2e = [], []
-            for i in range(6):
-                t0 = time.time()
-                t = kx.pciids_load(one)
-                rows2 = kx.lookup(t, q2)
-                dt = (time.time() - t0) * 1e6
-                t.free()
-                t = kx.pciids_load(one)
-                tm = kx.timings()
-                t.free()
-                if i > 0:
-                    c2_e2e.append(dt)
-                    c2_dev.append((tm[K.binding.T_PARSE] + tm[K.binding.T_RESOLVE] + tm[K.binding.T_FINALIZE]) * 1e3)
-            line["aux"] = {
-                "cfg2_pci_ids_once": {"text_bytes": len(text), "lookups": int(len(q2)), "hits": int((rows2 >= 0).sum()),
-                                      "device_us_parse_resolve_finalize": float(np.min(c2_dev)),
-                                      "e2e_us_host_text_to_rows": float(np.min(c2_e2e)),
-                                      "note": "1.4 MB is L2 resident and launch/latency bound: far below the roofline by construction"},
-                "cfg3_classify": {"records": len(recs), "accepted": int(res["n_accepted"]), "kernel_ms": float(np.min(cls_ms[1:])),
-                                  "records_per_s": len(recs) / (float(np.min(cls_ms[1:])) * 1e-3),
-                                  "algorithmic_gbs": len(recs) * 68 / (float(np.min(cls_ms[1:])) * 1e-3) / 1e9},
-                "cfg5_cdi_json": {"devices": len(devs), "bytes": len(j), "kernel_ms": float(np.min(emit_j_ms[1:])),
-                                  "gbs": (len(j) + 32 * len(devs)) / (float(np.min(emit_j_ms[1:])) * 1e-3) / 1e9},
-                "cfg5_cdi_yaml": {"devices": len(devs), "bytes": len(y), "kernel_ms": float(np.min(emit_y_ms[1:])),
-                                  "gbs": (len(y) + 32 * len(devs)) / (float(np.min(emit_y_ms[1:])) * 1e-3) / 1e9},
-            }
-        if world == 1 and not args.no_cpu_baseline:
+        other = [m for m in modes if m != args.scaling]
+        if other:
+            o = results[other[0]]
+            line[other[0] + "_scaling"] = {
+                "value": o["value"], "unit": "GB/s", "ms_per_step": o["ms_per_step"], "kernel_ms": o["kernel_ms"],
+                "job_bytes": int(n * world if other[0] == "weak" else n), "e2e": o["e2e"], "gpu_launches": o["launches"],
+                "parity_checked": bool(o["parity_checked"]), "settle_steps": o["settle_steps"],
+                "note": ("every rank parses its own x1000 shard (1.458 GB) of one logical x(1000*N) text and joins its own 2^20 keys"
+                         if other[0] == "weak" else "the fixed 1.458 GB text over N shards, 2^20 keys over N slices")}
+    if world == 1:
+        w = results["_w"]
+        if rank == 0 and not args.no_aux:
+            line["aux"] = aux_configs(kx, K, W, text, present, peak)
+        if rank == 0 and not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()
             threads = host_threads()
@@ -401,14 +523,73 @@ def main():
                           "(C restatement of the Go reference; Go toolchain absent), %.1f s wall on all host threads; value = job "
                           "text bytes / (sample time x 2^20 / sample keys); scan_gbs = bytes the scanners consumed "
                           "per second (the reference re-reads the text for every key)" % (nk, dt)}
-            dtb, parse_s, _ = O.bench_parse_once(h_text, keys[:1 << 16])
-            line["cpu_best"] = {"parse_once_gbs": n / parse_s / 1e9, "cores": 1,
-                                "note": "honest best CPU: one sequential pass building a table, then binary-search probes"}
+            best = []
+            for th in sorted({1, threads}):
+                dtb, parse_s, offs = O.bench_parse_mt(h_text, keys, th)
+                best.append({"cores": th, "parse_gbs": n / parse_s / 1e9, "job_gbs": n / dtb / 1e9, "job_s": dtb})
+            line["cpu_best"] = {"runs": best, "job_gbs_all_cores": best[-1]["job_gbs"], "cores": threads,
+                                "note": "honest best CPU on the SAME job: single pass per thread over vendor-line shards "
+                                        "(dead blocks skipped like on the GPU), first anchors min-merged, 2^20 binary-search "
+                                        "probes on all threads; host memory only, no PCIe -- compare with e2e.value"}
+        free_workload(w)
+    if rank == 0:
         emit_line(real_stdout, line)
     kx.pinned_free(h_ptr)
     if dist is not None:
         kx.comm_destroy()
         dist.destroy_process_group()
+    kx.close()
+
+
+def aux_configs(kx, K, W, text, present, peak):
+    """The other rows of the hot path through the host-buffer ABI; device
+    time of their kernels from the library's CUDA events; each with its own roofline.  Not part of `value`."""
+    B = K.binding
+    recs = W.cfg3_records(present)
+    devs = W.cfg5_devices()
+    cls_ms, emit_j_ms, emit_y_ms = [], [], []
+    for _ in range(5):
+        res = kx.classify(recs)
+        cls_ms.append(kx.timings()[B.T_CLASSIFY])
+        j = kx.cdi_emit(B.FMT_JSON, devs)
+        emit_j_ms.append(kx.timings()[B.T_EMIT])
+        y = kx.cdi_emit(B.FMT_YAML, devs)
+        emit_y_ms.append(kx.timings()[B.T_EMIT])
+    # configs[1] (cfg2): the real utils/pci.ids once + 1024 lookups -- latency, not bandwidth
+    one = np.frombuffer(text, np.uint8)
+    q2 = W.cfg2_queries(present)
+    c2_dev, c2_e2e = [], []
+    for i in range(8):
+        t0 = time.time()
+        t = kx.pciids_load(one)
+        rows2 = kx.lookup(t, q2)
+        dt = (time.time() - t0) * 1e6
+        t.free()
+        t = kx.pciids_load(one)
+        tm = kx.timings()
+        t.free()
+        if i > 1:
+            c2_e2e.append(dt)
+            c2_dev.append((tm[B.T_PARSE] + tm[B.T_RESOLVE] + tm[B.T_FINALIZE]) * 1e3)
+
+    def roof(alg_bytes, ms, kernel):
+        a = alg_bytes / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "kernel": kernel,
+                "algorithmic_bytes_per_launch": int(alg_bytes), "traffic": None}
+    cm, jm, ym = float(np.min(cls_ms[1:])), float(np.min(emit_j_ms[1:])), float(np.min(emit_y_ms[1:]))
+    return {
+        "cfg2_pci_ids_once": {"text_bytes": len(text), "lookups": int(len(q2)), "hits": int((rows2 >= 0).sum()),
+                              "device_us_parse_resolve_finalize": float(np.min(c2_dev)),
+                              "e2e_us_host_text_to_rows": float(np.min(c2_e2e)),
+                              "note": "1.4 MB is L2 resident and launch/latency bound: far below the roofline by construction"},
+        "cfg3_classify": {"records": len(recs), "accepted": int(res["n_accepted"]), "kernel_ms": cm,
+                          "records_per_s": len(recs) / (cm * 1e-3),
+                          "roofline": roof(len(recs) * 68, cm, "classify kernels (64 B record read + 4 B busIndex write)")},
+        "cfg5_cdi_json": {"devices": len(devs), "bytes": len(j), "kernel_ms": jm,
+                          "roofline": roof(len(j) + 32 * len(devs), jm, "kxemit (output bytes + 32 B record read)")},
+        "cfg5_cdi_yaml": {"devices": len(devs), "bytes": len(y), "kernel_ms": ym,
+                          "roofline": roof(len(y) + 32 * len(devs), ym, "kxemit (output bytes + 32 B record read)")},
+    }
 
 
 if __name__ == "__main__":

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KXPU_ABI_VERSION 1
+#define KXPU_ABI_VERSION 2
 
 /* status codes */
 #define KXPU_OK             0
@@ -39,7 +39,7 @@ extern "C" {
 #define KXPU_E_NOGPU       -3  /* no CUDA device / not an sm_100 part */
 #define KXPU_E_NOSPACE     -4  /* caller buffer too small; required size was stored */
 #define KXPU_E_CAPACITY    -5  /* internal table capacity exceeded after growth limit */
-#define KXPU_E_NCCL        -6  /* NCCL missing or failed */
+#define KXPU_E_NCCL        -6  /* NCCL / peer-memory exchange missing, failed or timed out */
 #define KXPU_E_UNSUPPORTED -7  /* input outside the supported domain (documented per call) */
 #define KXPU_E_NOMEM       -8
 
@@ -144,22 +144,66 @@ int32_t kxpu_pciids_join_device(kxpu_ctx *ctx, const void *d_text, size_t n, con
 int32_t kxpu_names(kxpu_ctx *ctx, kxpu_table *t, const int32_t *rows, size_t n,
                    uint8_t *out, size_t cap, uint32_t *offsets, size_t *need);
 
-/* ------------------------------------------------- multi-GPU (one rank/GPU) */
+/* ------------------------------------------------------------- multi-GPU */
 
-/* NCCL is loaded lazily (dlopen libnccl.so.2); single-GPU users never need it. */
+/* The pci.ids text shards by vendor-id range: a cut may only fall where a
+ * TOP-LEVEL line starts (first byte neither '\t' nor '#'), so no vendor block spans two shards.
+ * Host-side planner: cuts_out[0] = 0 <= cuts_out[1] <= ... <= cuts_out[nranks] = n; rank r owns
+ * text[cuts_out[r] .. cuts_out[r+1]).  A few memchr calls per cut; not part of the parse. */
+int32_t kxpu_plan_shards(const uint8_t *text, size_t n, int32_t nranks, uint64_t *cuts_out /* nranks+1 */);
+
+/* --- one process per rank (torchrun-style launch).  NCCL is loaded lazily (dlopen libnccl.so.2);
+ * single-GPU users never need it.  kxpu_comm_init also maps every peer's exchange region through
+ * CUDA IPC; the data plane of the sharded load is then peer-memory stores over NVLink, NCCL is the
+ * fallback transport (KXPU_NO_P2P=1 forces it). */
 #define KXPU_COMM_ID_BYTES 128
 int32_t kxpu_comm_unique_id(uint8_t id_out[KXPU_COMM_ID_BYTES]);
 int32_t kxpu_comm_init(kxpu_ctx *ctx, int32_t nranks, int32_t rank,
                        const uint8_t id[KXPU_COMM_ID_BYTES]);
 int32_t kxpu_comm_destroy(kxpu_ctx *ctx);
 /* Collective.  Each rank passes its shard of one logical text: bytes
- * [global_base, global_base+n), cut where a top-level line (first byte neither '\t'
- * nor '#') starts, i.e. at a vendor-id boundary.  Every rank parses its shard,
- * the hit rows (key, line offset, anchor offset, sanitised name) are exchanged with
- * ONE ncclAllGather and min-merged, and every rank returns the same table, equal to
- * kxpu_pciids_load on the concatenated text. */
+ * [global_base, global_base+n) as planned by kxpu_plan_shards (16-byte aligned device pointer).
+ * Every rank parses its shard; "first anchor wins" (device_plugin.go:263-267) is decided across
+ * shards by an all-reduce(min) of the per-vendor first anchors, then only the winning rows and
+ * their sanitised names are exchanged and inserted, and every rank returns the same table, equal
+ * to kxpu_pciids_load on the concatenated text (same row handles on every rank).
+ * A time-out (a rank missing for 4 s) or a CUDA error leaves the communicator unusable:
+ * KXPU_E_NCCL until kxpu_comm_destroy + kxpu_comm_init. */
 int32_t kxpu_pciids_load_sharded(kxpu_ctx *ctx, const void *d_text_shard, size_t n,
                                  uint64_t global_base, kxpu_table **out);
+/* Collective: the sharded load plus the join of BASELINE configs[3].  Rank r probes its slice
+ * d_keys[0..nq) = keys[key_offset .. key_offset+nq) of one logical key array of nq_total keys and
+ * stores every hit into every rank's result buffer (the all-gather of hits rides on the probe
+ * kernel); d_rows_all (device, [nq_total], may be NULL) receives all nq_total row handles on
+ * every rank.  nq_total <= 2^21 on the peer-memory transport; the NCCL transport needs equal
+ * slices in rank order. */
+int32_t kxpu_pciids_join_sharded(kxpu_ctx *ctx, const void *d_text_shard, size_t n, uint64_t global_base,
+                                 const uint32_t *d_keys, size_t nq, size_t key_offset, size_t nq_total,
+                                 int32_t *d_rows_all, kxpu_table **out);
+
+/* --- one process, N GPUs: what the reference's single Go process (cmd/main.go:5-7) binds.
+ * The contexts of a group see each other's exchange regions through direct peer pointers
+ * (cudaDeviceEnablePeerAccess), no IPC, no NCCL.  The same ordinal may appear more than once
+ * (several contexts on one GPU: used by the single-GPU parity tests of the sharded path). */
+typedef struct kxpu_multi kxpu_multi;
+int32_t kxpu_ctx_create_multi(const int32_t *ordinals, int32_t n, kxpu_multi **out);
+int32_t kxpu_multi_destroy(kxpu_multi *m);          /* destroys its contexts too */
+int32_t kxpu_multi_size(kxpu_multi *m);
+kxpu_ctx *kxpu_multi_ctx(kxpu_multi *m, int32_t i);  /* borrowed: usable with every single-ctx call */
+typedef struct kxpu_shard {
+    const void     *d_text;      /* shard on GPU i, 16-byte aligned                    */
+    size_t          n;
+    uint64_t        global_base;
+    const uint32_t *d_keys;      /* key slice of rank i on GPU i (NULL: no join)       */
+    size_t          nq;
+    size_t          key_offset;
+    int32_t        *d_rows_all;  /* [nq_total] on GPU i, may be NULL                   */
+} kxpu_shard;
+/* kxpu_pciids_join_sharded for all ranks of the group from ONE host thread: the kernels of every
+ * rank are enqueued phase by phase, then all streams are awaited once.  tables_out[i] belongs to
+ * kxpu_multi_ctx(m, i).  nq_total = 0: load only. */
+int32_t kxpu_multi_pciids_join(kxpu_multi *m, const kxpu_shard *shards /* [size] */, size_t nq_total,
+                               kxpu_table **tables_out /* [size] */);
 
 /* ----------------------------------------------- S1/S4: discovery classify */
 

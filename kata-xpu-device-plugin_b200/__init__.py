@@ -4,11 +4,11 @@ This package holds only what the hot path needs:
   csrc/      CUDA kernels for sm_100a + the C ABI (include/kxpu.h) -> lib/libkxpu.so
   host/      host-side mirror of the reference's discovery / CDI / Allocate logic (C++)
   binding.py ctypes binding of the C ABI (what the Go cgo shim of INTEGRATION.md does)
-  plugin.py  Python mirror of the reference operator interface for tests and bench
+  sharding.py thin wrapper over kxpu_plan_shards (kept for the CPU tests of the shard planner)
   workloads.py synthetic inputs of BASELINE.json configs[0..4]
 
 The directory name contains '-', so import it through the repo-root shim `kxpu_b200`.
 There is NO CPU fallback: if lib/libkxpu.so or a B200 is missing, every compute call
 raises KxpuError.
 """
-from .binding import Kxpu, KxpuError, lib_path, load_library  # noqa: F401
+from .binding import Kxpu, KxpuError, KxpuMulti, lib_path, load_library, plan_shards  # noqa: F401

@@ -34,7 +34,9 @@ ABI_SYMBOLS = [
     "kxpu_dev_replicate", "kxpu_pinned_alloc", "kxpu_pinned_free", "kxpu_sync", "kxpu_pciids_load",
     "kxpu_pciids_load_device", "kxpu_table_free", "kxpu_table_rows", "kxpu_table_export", "kxpu_lookup",
     "kxpu_lookup_device", "kxpu_pciids_join_device", "kxpu_names", "kxpu_comm_unique_id", "kxpu_comm_init", "kxpu_comm_destroy",
-    "kxpu_pciids_load_sharded", "kxpu_classify", "kxpu_cdi_emit", "kxpu_alloc_names", "kxpu_lw_encode",
+    "kxpu_pciids_load_sharded", "kxpu_pciids_join_sharded", "kxpu_plan_shards", "kxpu_ctx_create_multi", "kxpu_multi_destroy",
+    "kxpu_multi_size", "kxpu_multi_ctx", "kxpu_multi_pciids_join", "kxpu_classify", "kxpu_cdi_emit", "kxpu_alloc_names",
+    "kxpu_lw_encode",
 ]
 
 
@@ -43,6 +45,11 @@ class ClassifyOut(C.Structure):
                 ("group_members", C.c_void_p), ("dev_ids", C.c_void_p), ("dev_off", C.c_void_p),
                 ("dev_groups", C.c_void_p), ("n_accepted", C.c_uint32), ("n_groups", C.c_uint32),
                 ("n_devids", C.c_uint32)]
+
+
+class Shard(C.Structure):
+    _fields_ = [("d_text", C.c_void_p), ("n", C.c_size_t), ("global_base", C.c_uint64), ("d_keys", C.c_void_p),
+                ("nq", C.c_size_t), ("key_offset", C.c_size_t), ("d_rows_all", C.c_void_p)]
 
 
 class KxpuError(RuntimeError):
@@ -99,6 +106,13 @@ def load_library():
         "kxpu_comm_init": (i32, [vp, i32, i32, vp]),
         "kxpu_comm_destroy": (i32, [vp]),
         "kxpu_pciids_load_sharded": (i32, [vp, vp, sz, u64, C.POINTER(vp)]),
+        "kxpu_pciids_join_sharded": (i32, [vp, vp, sz, u64, vp, sz, sz, sz, vp, C.POINTER(vp)]),
+        "kxpu_plan_shards": (i32, [vp, sz, i32, vp]),
+        "kxpu_ctx_create_multi": (i32, [vp, i32, C.POINTER(vp)]),
+        "kxpu_multi_destroy": (i32, [vp]),
+        "kxpu_multi_size": (i32, [vp]),
+        "kxpu_multi_ctx": (vp, [vp, i32]),
+        "kxpu_multi_pciids_join": (i32, [vp, C.POINTER(Shard), sz, C.POINTER(vp)]),
         "kxpu_classify": (i32, [vp, vp, sz, C.POINTER(ClassifyOut)]),
         "kxpu_cdi_emit": (i32, [vp, i32, vp, sz, vp, sz, C.POINTER(sz)]),
         "kxpu_alloc_names": (i32, [vp, vp, sz, vp, sz, vp, C.POINTER(sz)]),
@@ -134,8 +148,12 @@ class Table:
 class Kxpu:
     """One context bound to one GPU (== one kxpu_ctx)."""
 
-    def __init__(self, ordinal=0):
+    def __init__(self, ordinal=0, _borrowed=None):
         self.L = load_library()
+        self.borrowed = _borrowed is not None
+        if self.borrowed:  # a context of a KxpuMulti group: destroyed with the group
+            self.ctx = C.c_void_p(_borrowed)
+            return
         ctx = C.c_void_p()
         rc = self.L.kxpu_ctx_create(ordinal, C.byref(ctx))
         if rc != KXPU_OK:
@@ -143,9 +161,9 @@ class Kxpu:
         self.ctx = ctx
 
     def close(self):
-        if self.ctx:
+        if self.ctx and not self.borrowed:
             self.L.kxpu_ctx_destroy(self.ctx)
-            self.ctx = None
+        self.ctx = None
 
     def _chk(self, rc):
         if rc != KXPU_OK:
@@ -226,6 +244,12 @@ class Kxpu:
     def pciids_load_sharded(self, d_text, n, global_base):
         h = C.c_void_p()
         self._chk(self.L.kxpu_pciids_load_sharded(self.ctx, d_text, n, global_base, C.byref(h)))
+        return Table(self, h)
+
+    def pciids_join_sharded(self, d_text, n, global_base, d_keys, nq, key_offset, nq_total, d_rows_all):
+        h = C.c_void_p()
+        self._chk(self.L.kxpu_pciids_join_sharded(self.ctx, d_text, n, global_base, d_keys, nq, key_offset, nq_total,
+                                                  d_rows_all, C.byref(h)))
         return Table(self, h)
 
     def table_export(self, table):
@@ -322,3 +346,52 @@ class Kxpu:
         self._chk(self.L.kxpu_lw_encode(self.ctx, _ptr(groups), _ptr(healthy), len(groups), _ptr(out), need.value,
                                         C.byref(got)))
         return out[:got.value].tobytes()
+
+
+def plan_shards(text, nranks):
+    """kxpu_plan_shards: [(start, end)] * nranks, cuts at top-level (vendor) line starts."""
+    L = load_library()
+    a = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+    cuts = np.zeros(nranks + 1, np.uint64)
+    rc = L.kxpu_plan_shards(a.ctypes.data if a.size else None, a.size, nranks, cuts.ctypes.data)
+    if rc != KXPU_OK:
+        raise KxpuError(rc, L.kxpu_strerror(rc).decode())
+    return [(int(cuts[i]), int(cuts[i + 1])) for i in range(nranks)]
+
+
+class KxpuMulti:
+    """kxpu_ctx_create_multi: N contexts of ONE process (what a single Go host binds)."""
+
+    def __init__(self, ordinals):
+        self.L = load_library()
+        arr = (C.c_int32 * len(ordinals))(*ordinals)
+        h = C.c_void_p()
+        rc = self.L.kxpu_ctx_create_multi(arr, len(ordinals), C.byref(h))
+        if rc != KXPU_OK:
+            raise KxpuError(rc, self.L.kxpu_strerror(rc).decode() + " (no CPU fallback exists)")
+        self.handle = h
+        self.ctxs = [Kxpu(_borrowed=self.L.kxpu_multi_ctx(h, i)) for i in range(len(ordinals))]
+
+    def __len__(self):
+        return int(self.L.kxpu_multi_size(self.handle))
+
+    def pciids_join(self, shards, nq_total=0):
+        """shards: one dict per rank with d_text, n, global_base and optionally d_keys, nq, key_offset, d_rows_all."""
+        n = len(self.ctxs)
+        arr = (Shard * n)()
+        for i, s in enumerate(shards):
+            arr[i] = Shard(s["d_text"], s["n"], s["global_base"], s.get("d_keys"), s.get("nq", 0), s.get("key_offset", 0),
+                           s.get("d_rows_all"))
+        tabs = (C.c_void_p * n)()
+        rc = self.L.kxpu_multi_pciids_join(self.handle, arr, nq_total, tabs)
+        if rc != KXPU_OK:
+            msgs = "; ".join(self.L.kxpu_last_error(k.ctx).decode() for k in self.ctxs)
+            raise KxpuError(rc, "%s: %s" % (self.L.kxpu_strerror(rc).decode(), msgs))
+        return [Table(self.ctxs[i], C.c_void_p(tabs[i])) for i in range(n)]
+
+    def close(self):
+        if self.handle:
+            for k in self.ctxs:
+                k.ctx = None
+            self.L.kxpu_multi_destroy(self.handle)
+            self.handle = None

@@ -1,55 +1,66 @@
-// comm.cu -- multi-GPU pci.ids load: one rank per GPU, shards cut at vendor-line boundaries,
-// ONE ncclAllGather of hit rows over NVLink, then a min-merge on every rank.
+// comm.cu -- multi-GPU pci.ids load + join: one rank per GPU (one process per rank, or one
+// process driving all ranks through kxpu_ctx_create_multi), shards cut at vendor-line boundaries.
 //
-// BASELINE.json configs[3] / SURVEY.md 8(e): every rank parses its byte range of one logical
-// text (offsets are GLOBAL: global_base + local), which yields for every (vendor,device) key
-// the earliest candidate line of the shard, and for every vendor prefix its earliest anchor.
-// Candidates of all ranks are exchanged as fixed-capacity slabs
-//     [header | key rows | vendor rows | sanitised names]
-// and folded into a fresh table with the same atomicMin rule the parse kernel uses, so the
-// result equals kxpu_pciids_load on the concatenated text.  The payload is ~1 MB per rank
-// (18 856 rows x 32 B + 0.8 MB of names for pci.ids), i.e. latency bound on NVSwitch.
+// BASELINE.json configs[3] / SURVEY.md 8(e).  Every rank parses its byte range of one logical
+// text with GLOBAL offsets, which yields for every (vendor,device) key the earliest candidate
+// line of the shard and for every vendor prefix its earliest anchor.  "First anchor wins"
+// (device_plugin.go:263-267) is then decided across shards in two exchange phases:
 //
-// NCCL is loaded lazily with dlopen: a single-GPU deployment never needs libnccl.
+//   A  all-reduce(min) of vendor_first (+ the bufio.ErrTooLong cut-off and status bits): every
+//      rank atomicMin's its local minima straight into every rank's exchange region over NVLink
+//      (peer-memory stores; ~2 400 x 8 B per rank for pci.ids).  After phase A every rank knows
+//      the global first anchor of every vendor id, so a row is a WINNER iff its anchor equals
+//      it -- and winners are globally unique per key (the first block sits in exactly one shard).
+//   B  winners only: each rank sanitises the names of its winner rows and pushes rows + names
+//      into its slab in every rank's region.  Shards that hold no first block push nothing.
+//      Every rank then inserts the winners of all ranks into the table it parsed into -- no
+//      second table, no min-merge, row handles are global (rank prefix + index).
+//   C  (join) every rank probes its slice of the keys and stores each result into every rank's
+//      result buffer: the all-gather of hits rides on the probe kernel.
+//
+// A phase boundary is a flag per (phase, buffer, rank) in every region, raised by the last CTA
+// of the pushing kernel after a system fence, and a one-warp wait kernel.  Two buffers alternate
+// by epoch; a buffer is cleared one epoch ahead, before this rank raises the flag that lets its
+// peers move on (so a peer can never push into a buffer that is still being cleared or read).
+// The epoch is bumped before anything can fail, statuses travel WITH the data (min-encoded words
+// in phase A, slab headers in phase B), so every rank takes the same retry decision; a time-out
+// or a CUDA error marks the exchange broken (re-init required).
+//
+// Transports: peer memory (CUDA IPC mappings across processes, direct pointers inside one
+// process) is the product path; NCCL (ncclAllReduce(min) / ncclAllGather, loaded lazily with
+// dlopen) runs the same kernels against a local staging region when peer mapping is impossible
+// (KXPU_NO_P2P=1 forces it) or a slab outgrows the fixed peer region.
 #include <dlfcn.h>
 
 #include <algorithm>
 #include <new>
 
-#include "common.cuh"
-#include "slab.cuh"
-#include "table.cuh"
+#include "internal.cuh"
+#include "parse_common.cuh"
 
-// from api.cu
-struct kxpu_table;
-int32_t kx_build_table(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, unsigned long long base,
-                       unsigned long long carry_in, int check_valid, kxpu_table **out);
-int32_t kx_table_from_gather(kxpu_ctx *ctx, void *d_gather, int nranks, size_t slab_stride, kxcomm::SlabCaps caps,
-                             kxpu_table **out, bool own_names, const uint32_t *peer_timeout);
-void kx_table_local_view(kxpu_table *t, KxTableDev *dev, uint32_t *cap, uint32_t *n_rows, uint32_t *blob_used,
-                         const uint32_t **row_key, const unsigned long long **row_line, const unsigned long long **row_anchor,
-                         const uint32_t **row_name_off, const uint32_t **row_name_len, const uint8_t **blob);
-void kx_table_release(kxpu_ctx *ctx, kxpu_table *t);
+namespace kxx {
 
-namespace kxcomm {
-
+// ------------------------------------------------------------------ NCCL (lazy)
 typedef int (*fn_get_unique_id)(void *);
-typedef int (*fn_comm_init_rank)(void **, int, char[128], int);  // ncclUniqueId is passed by value (128 bytes)
 typedef int (*fn_comm_destroy)(void *);
 typedef int (*fn_all_gather)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*fn_all_reduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef const char *(*fn_err_string)(int);
+struct UniqueId { char internal[128]; };
+typedef int (*fn_comm_init_rank)(void **, int, UniqueId, int);  // ncclUniqueId is passed by value (128 bytes)
 
 struct NcclApi {
     void *handle = nullptr;
     fn_get_unique_id get_unique_id = nullptr;
-    void *comm_init_rank = nullptr;
+    fn_comm_init_rank comm_init_rank = nullptr;
     fn_comm_destroy comm_destroy = nullptr;
     fn_all_gather all_gather = nullptr;
+    fn_all_reduce all_reduce = nullptr;
     fn_err_string err_string = nullptr;
 };
-
 static NcclApi g_nccl;
 static std::mutex g_nccl_mu;
+constexpr int NCCL_UINT8 = 1, NCCL_UINT64 = 5, NCCL_MIN = 3;
 
 static bool nccl_load() {
     std::lock_guard<std::mutex> g(g_nccl_mu);
@@ -62,57 +73,700 @@ static bool nccl_load() {
     }
     if (!h) return false;
     g_nccl.get_unique_id = (fn_get_unique_id)dlsym(h, "ncclGetUniqueId");
-    g_nccl.comm_init_rank = dlsym(h, "ncclCommInitRank");
+    g_nccl.comm_init_rank = (fn_comm_init_rank)dlsym(h, "ncclCommInitRank");
     g_nccl.comm_destroy = (fn_comm_destroy)dlsym(h, "ncclCommDestroy");
     g_nccl.all_gather = (fn_all_gather)dlsym(h, "ncclAllGather");
+    g_nccl.all_reduce = (fn_all_reduce)dlsym(h, "ncclAllReduce");
     g_nccl.err_string = (fn_err_string)dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.comm_destroy || !g_nccl.all_gather) return false;
+    if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.comm_destroy || !g_nccl.all_gather || !g_nccl.all_reduce) return false;
     g_nccl.handle = h;
     return true;
 }
 
-struct UniqueId { char internal[128]; };
-typedef int (*fn_comm_init_rank_byval)(void **, int, UniqueId, int);
+// ------------------------------------------------------------------ exchange region
+constexpr uint32_t XS_GROW = 1u;           // a rank's table overflowed / is too full
+constexpr uint32_t XS_NEED_TRUNC = 2u;     // a rank saw a possible >= 64 KiB line: run again with exact cut-offs
+constexpr uint32_t XS_SLAB_OVERFLOW = 4u;  // a rank's winners outgrow the slab
+constexpr uint32_t XS_GROW_BLOB = 8u;      // a rank's name blob is too small
+constexpr int XS_BITS = 4;
 
-__global__ void __launch_bounds__(256) pack_rows_kernel(uint8_t *slab, SlabCaps caps, uint32_t n_rows,
-                                                        const uint32_t *row_key, const unsigned long long *row_line,
-                                                        const unsigned long long *row_anchor, const uint32_t *row_name_off,
-                                                        const uint32_t *row_name_len, const unsigned long long *trunc,
-                                                        uint32_t blob_used) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    SlabHeader *h = reinterpret_cast<SlabHeader *>(slab);
-    if (i == 0) {
-        h->n_rows = n_rows < caps.rows ? n_rows : caps.rows;
-        h->blob_bytes = blob_used;
-        h->trunc = *trunc;
-        h->reserved = 0;
-        if (n_rows > caps.rows || blob_used > caps.blob) atomicOr(&h->overflow, 1u);
+constexpr int A_TRUNC = 65536;       // phase-A block: u64 [65536] vendor_first | trunc | XS_BITS status words | pad
+constexpr int A_STATUS0 = 65537;     // status bit k is set iff word A_STATUS0 + k == 0 (so that min all-reduces it)
+constexpr int A_WORDS = 65536 + 8;
+constexpr size_t FLAGS_BYTES = 1024;  // u32 flag[3 phases][2 buffers][KX_MAX_RANKS]
+
+struct XCaps { uint32_t rows, blob, join; };  // per-rank slab rows / name bytes, keys of one sharded join
+
+struct SlabHeader {  // 64 bytes
+    uint32_t n_rows, blob_bytes, status, nkeys;
+    uint32_t pad[12];
+};
+struct SlabRow {  // 32 bytes: one winner (vendor,device) row of the shard
+    uint32_t key, name_len;
+    unsigned long long line, anchor;
+    uint32_t name_off, pad;
+};
+
+struct XLayout {
+    size_t o_a[2], o_slab[2], slab_stride, o_res[2], total;
+};
+__host__ __device__ static inline size_t x_align(size_t x) { return (x + 255) / 256 * 256; }
+static XLayout x_layout(const XCaps &c, int R) {
+    XLayout L;
+    size_t off = FLAGS_BYTES;
+    for (int b = 0; b < 2; b++) { L.o_a[b] = off; off = x_align(off + (size_t)A_WORDS * 8); }
+    L.slab_stride = x_align(sizeof(SlabHeader) + (size_t)c.rows * sizeof(SlabRow) + c.blob + 16);
+    for (int b = 0; b < 2; b++) { L.o_slab[b] = off; off += (size_t)R * L.slab_stride; }
+    for (int b = 0; b < 2; b++) { L.o_res[b] = off; off = x_align(off + (size_t)c.join * 4); }
+    L.total = off;
+    return L;
+}
+__host__ __device__ static inline size_t slab_rows_off() { return sizeof(SlabHeader); }
+__host__ __device__ static inline size_t slab_blob_off(uint32_t rows_cap) { return sizeof(SlabHeader) + (size_t)rows_cap * sizeof(SlabRow); }
+__host__ __device__ static inline size_t flag_off(int phase, int b, int rank) { return (size_t)((phase * 2 + b) * KX_MAX_RANKS + rank) * 4; }
+
+static const XCaps kPeerCaps{65536u, 2u << 20, 1u << 21};
+
+struct Targets {  // where a push goes: every rank's region (peer memory) or this rank's staging region (NCCL)
+    uint8_t *region[KX_MAX_RANKS];
+    int n;
+};
+
+}  // namespace kxx
+
+struct KxExchange {
+    int nranks = 1, rank = 0;
+    bool p2p = false;     // peer-memory transport available
+    bool ipc = false;     // peers mapped through CUDA IPC (else direct pointers of this process)
+    bool broken = false;  // a time-out / CUDA error desynchronised the ranks: re-init required
+    bool use_nccl = false;  // transport of the current/next attempt
+    uint8_t *local = nullptr;
+    uint8_t *peer[KX_MAX_RANKS] = {};
+    kxx::XLayout L{};
+    kxx::XCaps caps{};
+    uint32_t epoch = 0;
+    uint32_t *scratch = nullptr;  // device: [0..2] last-CTA counters of the three pushing kernels, [8] time-out flag
+    // uniform across ranks (only changed by decisions every rank takes alike)
+    uint32_t x_cap = 1u << 16, x_blob_cap = 4u << 20;
+    // NCCL transport: staging region with the same layout (R slabs contiguous = all-gather target)
+    uint8_t *stage = nullptr;
+    uint8_t *send_slab = nullptr;
+    kxx::XLayout SL{};
+    kxx::XCaps scaps{};
+};
+
+namespace kxx {
+
+// ------------------------------------------------------------------ kernels
+struct XaParams {
+    Targets tg;
+    uint8_t *mine;            // my region (the next buffer's phase-A block is cleared here)
+    size_t o_a, o_a_next;     // phase-A block of this / the next epoch inside a region
+    int clear_next;
+    size_t o_flag;            // my phase-A flag inside a region (peer transport)
+    int raise_flags;
+    uint32_t epoch;
+    const unsigned long long *vendor_first, *trunc;
+    const uint32_t *counters;
+    uint32_t max_keys;
+    int have_trunc;
+    uint32_t *done;
+};
+
+// Phase A: vendor_first / cut-off / status of this shard, min-reduced into every rank's region.
+__global__ void __launch_bounds__(256) xa_push_kernel(const XaParams P) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;  // 65536 threads
+    if (P.clear_next) {
+        unsigned long long *nx = reinterpret_cast<unsigned long long *>(P.mine + P.o_a_next);
+        nx[v] = KX_NO_OFF;
+        if (v < (uint32_t)(A_WORDS - 65536)) nx[65536 + v] = KX_NO_OFF;
     }
-    if (i >= n_rows || i >= caps.rows) return;
-    SlabRow *rows = reinterpret_cast<SlabRow *>(slab + sizeof(SlabHeader));
-    SlabRow r;
-    r.key = row_key[i]; r.name_len = row_name_len[i]; r.line = row_line[i]; r.anchor = row_anchor[i];
-    r.name_off = row_name_off[i]; r.pad = 0;
-    rows[i] = r;
+    const unsigned long long f = P.vendor_first[v];
+    if (f != KX_NO_OFF)
+        for (int q = 0; q < P.tg.n; q++) atomicMin(reinterpret_cast<unsigned long long *>(P.tg.region[q] + P.o_a) + v, f);
+    if (v == 0) {
+        const unsigned long long t = *P.trunc;
+        uint32_t st = 0;
+        if (P.counters[KX_C_OVERFLOW] || P.counters[KX_C_NKEYS] > P.max_keys) st |= XS_GROW;
+        if (P.counters[KX_C_LONGLINE_HINT] && !P.have_trunc) st |= XS_NEED_TRUNC;
+        for (int q = 0; q < P.tg.n; q++) {
+            unsigned long long *a = reinterpret_cast<unsigned long long *>(P.tg.region[q] + P.o_a);
+            if (t != KX_NO_OFF) atomicMin(a + A_TRUNC, t);
+            for (int k = 0; k < XS_BITS; k++)
+                if ((st >> k) & 1u) atomicMin(a + A_STATUS0 + k, 0ull);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(P.done, 1u);
+        if (prev == gridDim.x - 1u) {
+            *P.done = 0u;
+            __threadfence_system();
+            if (P.raise_flags)
+                for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[q] + P.o_flag) = P.epoch;
+            __threadfence_system();
+        }
+    }
 }
 
-__global__ void __launch_bounds__(256) pack_vendors_kernel(uint8_t *slab, SlabCaps caps, const unsigned long long *vendor_first) {
-    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;  // 65536 threads
-    SlabHeader *h = reinterpret_cast<SlabHeader *>(slab);
-    unsigned long long f = vendor_first[v];
-    if (f == KX_NO_OFF) return;
-    uint32_t idx = atomicAdd(&h->n_vendors, 1u);
-    if (idx >= caps.vendors) { atomicOr(&h->overflow, 2u); return; }
-    SlabVendor *vs = reinterpret_cast<SlabVendor *>(slab + sizeof(SlabHeader) + (size_t)caps.rows * sizeof(SlabRow));
-    vs[idx].vendor = v; vs[idx].pad = 0; vs[idx].first = f;
+// one warp: lane q waits for rank q's flag of this epoch
+__global__ void wait_flags_kernel(const uint32_t *flags, int nranks, uint32_t epoch, uint32_t *timeout_flag) {
+    const int q = threadIdx.x;
+    if (q < nranks) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<const volatile uint32_t *>(&flags[q]) != epoch) {
+            __nanosleep(100);
+            if (clock64() - t0 > 8000000000ll) { *timeout_flag = 1u; break; }  // ~4 s: a peer died or the ranks lost step
+        }
+    }
+    __threadfence_system();
 }
 
-}  // namespace kxcomm
+struct XbParams {
+    Targets tg;
+    size_t o_slab;  // my slab inside a region
+    uint32_t rows_cap, blob_cap;
+    size_t o_flag;
+    int raise_flags;
+    uint32_t epoch;
+    const uint32_t *counters;
+    const uint32_t *row_key, *row_name_off, *row_name_len;
+    const unsigned long long *row_line, *row_anchor;
+    const uint8_t *blob;
+    uint32_t *done;
+};
 
-#include "p2p.cuh"
+// Phase B: winner rows + their names, straight from the local table into this rank's slab in every
+// rank's region (32-byte row stores, 16-byte name stores over NVLink); the last CTA writes the header
+// and raises the flags.
+__global__ void __launch_bounds__(256) xb_push_kernel(const XbParams P) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    const uint32_t n_sel = P.counters[KX_C_NSEL], blob_used = P.counters[KX_C_BLOB_CURSOR];
+    uint32_t st = 0;
+    if (P.counters[KX_C_BLOB_OVERFLOW]) st |= XS_GROW_BLOB;
+    if (n_sel > P.rows_cap || blob_used > P.blob_cap) st |= XS_SLAB_OVERFLOW;
+    if (!st) {
+        for (size_t i = tid; i < n_sel; i += nth) {
+            SlabRow r;
+            r.key = P.row_key[i]; r.name_len = P.row_name_len[i]; r.line = P.row_line[i]; r.anchor = P.row_anchor[i];
+            r.name_off = P.row_name_off[i]; r.pad = 0;
+            for (int q = 0; q < P.tg.n; q++) reinterpret_cast<SlabRow *>(P.tg.region[q] + P.o_slab + slab_rows_off())[i] = r;
+        }
+        const size_t n16 = ((size_t)blob_used + 15) / 16;  // the blob lives in a 256-byte aligned arena with 16 bytes of slack
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(P.blob);
+        for (size_t i = tid; i < n16; i += nth) {
+            const uint4 x = s4[i];
+            for (int q = 0; q < P.tg.n; q++) reinterpret_cast<uint4 *>(P.tg.region[q] + P.o_slab + slab_blob_off(P.rows_cap))[i] = x;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(P.done, 1u);
+        if (prev == gridDim.x - 1u) {
+            *P.done = 0u;
+            __threadfence_system();
+            SlabHeader h;
+            memset(&h, 0, sizeof h);
+            h.n_rows = st ? 0u : n_sel;
+            h.blob_bytes = st ? 0u : blob_used;
+            h.status = st;
+            h.nkeys = P.counters[KX_C_NKEYS];
+            for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<SlabHeader *>(P.tg.region[q] + P.o_slab) = h;
+            __threadfence_system();
+            if (P.raise_flags)
+                for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[q] + P.o_flag) = P.epoch;
+            __threadfence_system();
+        }
+    }
+}
 
-using namespace kxcomm;
+struct MergeParams {
+    const uint8_t *slabs;  // slab of rank 0; rank r at + r * stride
+    size_t stride;
+    int R;
+    uint32_t slab_rows_cap;
+    const unsigned long long *a;  // my phase-A block (status words)
+    KxTableDev tab;
+    uint32_t *row_key, *row_name_off, *row_name_len;
+    unsigned long long *row_line, *row_anchor;
+    uint8_t *blob;
+    uint32_t rows_cap, blob_cap;
+    const uint32_t *timeout_flag;
+};
 
+// The winners of all ranks go into the table this rank parsed into: row arrays and names at their
+// global positions (rank prefix + index), key -> global row handle in the hash.  Winners are unique
+// per key, so this is an insert, not a min-merge.  Every rank computes the same summary
+// (KX_C_X*) from the same headers and takes the same retry decision from it.
+__global__ void __launch_bounds__(256) merge_kernel(const MergeParams P) {
+    __shared__ uint32_t rpre[KX_MAX_RANKS + 1], bpre[KX_MAX_RANKS + 1], s_status, s_maxkeys;
+    if (threadIdx.x == 0) {
+        uint32_t st = 0, mk = 0, racc = 0, bacc = 0;
+        for (int k = 0; k < XS_BITS; k++)
+            if (P.a[A_STATUS0 + k] == 0ull) st |= 1u << k;
+        for (int r = 0; r < P.R; r++) {
+            const SlabHeader *h = reinterpret_cast<const SlabHeader *>(P.slabs + (size_t)r * P.stride);
+            rpre[r] = racc; bpre[r] = bacc;
+            racc += h->n_rows;
+            bacc += (h->blob_bytes + 15u) & ~15u;
+            st |= h->status;
+            mk = h->nkeys > mk ? h->nkeys : mk;
+        }
+        rpre[P.R] = racc; bpre[P.R] = bacc;
+        if (P.timeout_flag && *P.timeout_flag) st |= 0x80000000u;
+        s_status = st; s_maxkeys = mk;
+        if (blockIdx.x == 0) {
+            P.tab.counters[KX_C_XSTATUS] = st;
+            P.tab.counters[KX_C_XROWS] = racc;
+            P.tab.counters[KX_C_XBLOB] = bacc;
+            P.tab.counters[KX_C_XMAXKEYS] = mk;
+        }
+    }
+    __syncthreads();
+    const uint32_t total_rows = rpre[P.R], total_b16 = bpre[P.R] / 16u;
+    // uniform on every rank: table capacities are kept equal across ranks (KxExchange::x_cap)
+    if (s_status != 0u || total_rows > P.rows_cap || bpre[P.R] > P.blob_cap || total_rows + s_maxkeys > P.tab.max_keys) return;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = tid; g < total_rows; g += nth) {
+        int r = 0;
+        while (r + 1 < P.R && g >= rpre[r + 1]) r++;
+        const uint8_t *slab = P.slabs + (size_t)r * P.stride;
+        const SlabRow row = reinterpret_cast<const SlabRow *>(slab + slab_rows_off())[g - rpre[r]];
+        P.row_key[g] = row.key; P.row_line[g] = row.line; P.row_anchor[g] = row.anchor;
+        P.row_name_off[g] = bpre[r] + row.name_off; P.row_name_len[g] = row.name_len;
+        const uint32_t slot = kxparse::table_claim(P.tab, row.key);
+        if (slot != 0xffffffffu) P.tab.slots[slot].row = (int32_t)g;
+    }
+    for (size_t j = tid; j < total_b16; j += nth) {
+        int r = 0;
+        while (r + 1 < P.R && j * 16u >= bpre[r + 1]) r++;
+        const uint8_t *src = P.slabs + (size_t)r * P.stride + slab_blob_off(P.slab_rows_cap);
+        reinterpret_cast<uint4 *>(P.blob)[j] = reinterpret_cast<const uint4 *>(src)[j - bpre[r] / 16u];
+    }
+}
+
+// rows that lost (their anchor is not the global first one) keep a handle from the local finalize
+// only if they were selected, and selection already used the global minima: nothing to undo.
+
+struct JoinParams {
+    const uint32_t *keys;
+    size_t n, key_offset;
+    const KxSlot *slots;
+    uint32_t cap, shift;
+    Targets tg;
+    size_t o_res, o_flag;
+    int raise_flags;
+    uint32_t epoch;
+    uint32_t *done;
+};
+
+// Phase C: probe this rank's key slice; every result goes into every rank's result buffer
+// (4-byte stores into peer memory, coalesced per warp) -- probe and all-gather of hits in one kernel.
+__global__ void __launch_bounds__(256) join_gather_kernel(const JoinParams P) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < P.n; i += stride) {
+        const int32_t row = kxparse::table_probe(P.slots, P.cap, P.shift, P.keys[i]);
+        for (int q = 0; q < P.tg.n; q++) reinterpret_cast<int32_t *>(P.tg.region[q] + P.o_res)[P.key_offset + i] = row;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(P.done, 1u);
+        if (prev == gridDim.x - 1u) {
+            *P.done = 0u;
+            __threadfence_system();
+            if (P.raise_flags)
+                for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[q] + P.o_flag) = P.epoch;
+            __threadfence_system();
+        }
+    }
+}
+
+__global__ void fill_ff_kernel(uint4 *p, size_t n16) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+        p[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+}
+
+// ------------------------------------------------------------------ region set-up
+static int32_t region_alloc(kxpu_ctx *ctx, KxExchange *x, const XCaps &caps) {
+    x->caps = caps;
+    x->L = x_layout(caps, x->nranks);
+    if (cudaMalloc((void **)&x->local, x->L.total) != cudaSuccess) { cudaGetLastError(); x->local = nullptr; return KXPU_E_NOMEM; }
+    bool ok = cudaMemsetAsync(x->local, 0, FLAGS_BYTES, ctx->stream) == cudaSuccess;
+    for (int b = 0; b < 2 && ok; b++) ok = cudaMemsetAsync(x->local + x->L.o_a[b], 0xff, (size_t)A_WORDS * 8, ctx->stream) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&x->scratch, 256) == cudaSuccess && cudaMemsetAsync(x->scratch, 0, 256, ctx->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); return KXPU_E_CUDA; }
+    return KXPU_OK;
+}
+
+static void exchange_free(kxpu_ctx *ctx) {
+    KxExchange *x = ctx->xch;
+    if (!x) return;
+    cudaSetDevice(ctx->device);
+    if (x->ipc)
+        for (int q = 0; q < x->nranks; q++)
+            if (q != x->rank && x->peer[q]) cudaIpcCloseMemHandle(x->peer[q]);
+    if (x->local) cudaFree(x->local);
+    if (x->scratch) cudaFree(x->scratch);
+    if (x->stage) cudaFree(x->stage);
+    if (x->send_slab) cudaFree(x->send_slab);
+    cudaGetLastError();
+    delete x;
+    ctx->xch = nullptr;
+}
+
+// Map every peer's exchange region through CUDA IPC (one process per rank).  Any failure leaves
+// p2p false on EVERY rank (the ranks agree through one more tiny all-gather): NCCL transport.
+static void ipc_setup(kxpu_ctx *ctx, KxExchange *x) {
+    x->p2p = false;
+    const int R = x->nranks;
+    if (R < 2 || R > KX_MAX_RANKS || getenv("KXPU_NO_P2P")) return;
+    bool ok = region_alloc(ctx, x, kPeerCaps) == KXPU_OK;
+    cudaIpcMemHandle_t mine, all[KX_MAX_RANKS];
+    memset(&mine, 0, sizeof mine);
+    ok = ok && cudaIpcGetMemHandle(&mine, x->local) == cudaSuccess;
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    uint8_t *d_x = nullptr;
+    if (cudaMalloc((void **)&d_x, hb * (size_t)(R + 1) + 64) != cudaSuccess) { d_x = nullptr; ok = false; }
+    uint8_t okbyte[KX_MAX_RANKS + 1] = {};
+    if (d_x) {  // exchange the handles with the communicator that exists already
+        cudaMemcpyAsync(d_x, &mine, hb, cudaMemcpyHostToDevice, ctx->stream);
+        const int nrc = g_nccl.all_gather(d_x, d_x + hb, hb, NCCL_UINT8, ctx->nccl_comm, ctx->stream);
+        cudaMemcpyAsync(all, d_x + hb, hb * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream);
+        if (nrc != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = false;
+    }
+    bool opened[KX_MAX_RANKS] = {};
+    if (ok) {
+        for (int q = 0; q < R && ok; q++) {
+            if (q == x->rank) { x->peer[q] = x->local; continue; }
+            void *pp = nullptr;
+            if (cudaIpcOpenMemHandle(&pp, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+            x->peer[q] = (uint8_t *)pp;
+            opened[q] = true;
+        }
+    }
+    if (d_x) {  // agreement: all ranks or none
+        const uint8_t mineok = ok ? 1 : 0;
+        uint8_t *d_ok = d_x + hb * (size_t)(R + 1);
+        cudaMemcpyAsync(d_ok, &mineok, 1, cudaMemcpyHostToDevice, ctx->stream);
+        const int nrc = g_nccl.all_gather(d_ok, d_ok + 16, 1, NCCL_UINT8, ctx->nccl_comm, ctx->stream);
+        cudaMemcpyAsync(okbyte, d_ok + 16, (size_t)R, cudaMemcpyDeviceToHost, ctx->stream);
+        if (nrc != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) ok = false;
+        for (int q = 0; q < R; q++) ok = ok && okbyte[q] == 1;
+        cudaFree(d_x);
+    }
+    if (!ok) {
+        for (int q = 0; q < R; q++)
+            if (opened[q]) cudaIpcCloseMemHandle(x->peer[q]);
+        memset(x->peer, 0, sizeof x->peer);
+        if (x->local) { cudaFree(x->local); x->local = nullptr; }
+        if (x->scratch) { cudaFree(x->scratch); x->scratch = nullptr; }
+        cudaGetLastError();
+        if (getenv("KXPU_TRACE_MERGE")) fprintf(stderr, "[kxpu] rank %d: peer-memory exchange unavailable, using NCCL\n", x->rank);
+        return;
+    }
+    x->ipc = true;
+    x->p2p = true;
+    if (getenv("KXPU_TRACE_MERGE")) fprintf(stderr, "[kxpu] rank %d: peer-memory exchange over %d ranks, %zu B per rank\n", x->rank, R, x->L.total);
+}
+
+// NCCL transport: a staging region of the same layout whose R slabs form the all-gather target
+static int32_t stage_reserve(kxpu_ctx *ctx, KxExchange *x, const XCaps &want) {
+    if (x->stage && x->scaps.rows >= want.rows && x->scaps.blob >= want.blob) return KXPU_OK;
+    cudaStreamSynchronize(ctx->stream);
+    if (x->stage) { cudaFree(x->stage); x->stage = nullptr; }
+    if (x->send_slab) { cudaFree(x->send_slab); x->send_slab = nullptr; }
+    if (!x->scratch && (cudaMalloc((void **)&x->scratch, 256) != cudaSuccess || cudaMemset(x->scratch, 0, 256) != cudaSuccess)) {
+        cudaGetLastError();
+        return KXPU_E_NOMEM;
+    }
+    x->scaps = want;
+    x->scaps.join = 0;
+    x->SL = x_layout(x->scaps, x->nranks);
+    if (cudaMalloc((void **)&x->stage, x->SL.total) != cudaSuccess || cudaMalloc((void **)&x->send_slab, x->SL.slab_stride) != cudaSuccess) {
+        cudaGetLastError();
+        KX_SET_ERR(ctx, "NCCL staging region (%zu B) could not be allocated", x->SL.total);
+        return KXPU_E_NOMEM;
+    }
+    return KXPU_OK;
+}
+
+// ------------------------------------------------------------------ one sharded load (+ join)
+struct ShardArgs {
+    const uint8_t *d_text;
+    size_t n;
+    unsigned long long base;
+    const uint32_t *d_keys;  // join slice of this rank (may be null)
+    size_t nq, key_offset, nq_total;
+    int32_t *d_rows_all;     // [nq_total] on this rank (may be null)
+};
+
+struct ShardOp {
+    kxpu_ctx *ctx = nullptr;
+    KxExchange *x = nullptr;
+    ShardArgs a{};
+    kxpu_table *t = nullptr;
+    bool have_trunc = false;
+    int b = 0;
+    uint32_t epoch = 0;
+    bool nccl = false;
+    int32_t rc = KXPU_OK;  // first failure of an enqueue phase (the remaining phases are skipped)
+};
+
+static Targets targets(const ShardOp &op) {
+    Targets tg;
+    memset(&tg, 0, sizeof tg);
+    if (op.nccl) { tg.n = 1; tg.region[0] = op.x->stage; }
+    else {
+        tg.n = op.x->nranks;
+        for (int q = 0; q < tg.n; q++) tg.region[q] = op.x->peer[q];
+    }
+    return tg;
+}
+static const XLayout &layout(const ShardOp &op) { return op.nccl ? op.x->SL : op.x->L; }
+static uint8_t *my_region(const ShardOp &op) { return op.nccl ? op.x->stage : op.x->local; }
+
+static void nccl_fail(ShardOp &op, const char *what, int nrc) {
+    KX_SET_ERR(op.ctx, "%s: %s", what, g_nccl.err_string ? g_nccl.err_string(nrc) : "error");
+    op.x->broken = true;
+    op.rc = KXPU_E_NCCL;
+}
+
+// phase 1: acquire + parse + push of the shard's minima.  Nothing here waits for a peer.
+static void shard_phase1(ShardOp &op) {
+    kxpu_ctx *ctx = op.ctx;
+    KxExchange *x = op.x;
+    op.rc = KXPU_OK;
+    op.t = nullptr;
+    op.epoch = ++x->epoch;  // before anything can fail: the ranks stay in step
+    op.nccl = x->use_nccl || !x->p2p;
+    op.b = op.nccl ? 0 : (int)(op.epoch & 1u);
+    if (x->broken) { KX_SET_ERR(ctx, "the exchange is broken (an earlier time-out or error): kxpu_comm_destroy + kxpu_comm_init"); op.rc = KXPU_E_NCCL; return; }
+    if ((reinterpret_cast<uintptr_t>(op.a.d_text) & 15u) != 0) { KX_SET_ERR(ctx, "device text pointer must be 16-byte aligned"); op.rc = KXPU_E_INVALID; return; }
+    if (op.a.base + op.a.n >= (1ull << 44)) { op.rc = KXPU_E_UNSUPPORTED; return; }
+    if (op.nccl) {
+        XCaps want{std::max<uint32_t>(x->x_cap, 65536u), std::max<uint32_t>(x->x_blob_cap / 2, 2u << 20), 0u};
+        if (x->scaps.rows > want.rows) want.rows = x->scaps.rows;
+        if (x->scaps.blob > want.blob) want.blob = x->scaps.blob;
+        op.rc = stage_reserve(ctx, x, want);
+        if (op.rc != KXPU_OK) return;
+        fill_ff_kernel<<<64, 256, 0, ctx->stream>>>((uint4 *)(x->stage + x->SL.o_a[0]), (size_t)A_WORDS * 8 / 16);
+        KX_LAUNCHED(ctx);
+    }
+    const uint32_t num_chunks = (uint32_t)((op.a.n + kxparse::CW - 1) / kxparse::CW);
+    op.rc = kx_table_acquire(ctx, x->x_cap, x->x_blob_cap, num_chunks, &op.t);
+    if (op.rc != KXPU_OK) return;
+    kxpu_table *t = op.t;
+    op.rc = kx_launch_parse(ctx, t, op.a.d_text, op.a.n, op.a.base, 0);
+    if (op.rc == KXPU_OK && op.have_trunc) op.rc = kx_launch_trunc(ctx, t, op.a.d_text, op.a.n, op.a.base);
+    if (op.rc != KXPU_OK) return;
+    if (ctx->stage_timing) cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE], ctx->stream);
+    const XLayout &L = layout(op);
+    XaParams P;
+    memset(&P, 0, sizeof P);
+    P.tg = targets(op);
+    P.mine = my_region(op);
+    P.o_a = L.o_a[op.b]; P.o_a_next = L.o_a[op.b ^ 1]; P.clear_next = op.nccl ? 0 : 1;
+    P.o_flag = flag_off(0, op.b, x->rank); P.raise_flags = op.nccl ? 0 : 1; P.epoch = op.epoch;
+    P.vendor_first = t->dev.vendor_first; P.trunc = t->dev.trunc; P.counters = t->dev.counters;
+    P.max_keys = t->dev.max_keys; P.have_trunc = op.have_trunc ? 1 : 0; P.done = x->scratch + 0;
+    xa_push_kernel<<<65536 / 256, 256, 0, ctx->stream>>>(P);
+    KX_LAUNCHED(ctx);
+}
+
+// phase 2: global minima are there -> winners, their names, push of the winner slab
+static void shard_phase2(ShardOp &op) {
+    if (op.rc != KXPU_OK) return;
+    kxpu_ctx *ctx = op.ctx;
+    KxExchange *x = op.x;
+    kxpu_table *t = op.t;
+    const XLayout &L = layout(op);
+    uint8_t *mine = my_region(op);
+    if (op.nccl) {
+        unsigned long long *a = reinterpret_cast<unsigned long long *>(mine + L.o_a[0]);
+        const int nrc = g_nccl.all_reduce(a, a, (size_t)A_WORDS, NCCL_UINT64, NCCL_MIN, ctx->nccl_comm, ctx->stream);
+        if (nrc != 0) { nccl_fail(op, "ncclAllReduce(min)", nrc); return; }
+    } else {
+        wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(mine + flag_off(0, op.b, 0)), x->nranks, op.epoch, x->scratch + 8);
+        KX_LAUNCHED(ctx);
+    }
+    const unsigned long long *a = reinterpret_cast<const unsigned long long *>(mine + L.o_a[op.b]);
+    op.rc = kx_launch_finalize(ctx, t, op.a.d_text, op.a.n, op.a.base, a, a + A_TRUNC);
+    if (op.rc != KXPU_OK) return;
+    XbParams P;
+    memset(&P, 0, sizeof P);
+    if (op.nccl) { P.tg.n = 1; P.tg.region[0] = x->send_slab; P.o_slab = 0; P.rows_cap = x->scaps.rows; P.blob_cap = x->scaps.blob; }
+    else { P.tg = targets(op); P.o_slab = L.o_slab[op.b] + (size_t)x->rank * L.slab_stride; P.rows_cap = x->caps.rows; P.blob_cap = x->caps.blob; }
+    P.o_flag = flag_off(1, op.b, x->rank); P.raise_flags = op.nccl ? 0 : 1; P.epoch = op.epoch;
+    P.counters = t->dev.counters; P.row_key = t->row_key; P.row_name_off = t->row_name_off; P.row_name_len = t->row_name_len;
+    P.row_line = t->row_line; P.row_anchor = t->row_anchor; P.blob = t->blob; P.done = x->scratch + 1;
+    xb_push_kernel<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(P);
+    KX_LAUNCHED(ctx);
+}
+
+// phase 3: winners of all ranks -> my table; join of my key slice, results to every rank
+static void shard_phase3(ShardOp &op) {
+    if (op.rc != KXPU_OK) return;
+    kxpu_ctx *ctx = op.ctx;
+    KxExchange *x = op.x;
+    kxpu_table *t = op.t;
+    const XLayout &L = layout(op);
+    uint8_t *mine = my_region(op);
+    if (op.nccl) {
+        const int nrc = g_nccl.all_gather(x->send_slab, mine + L.o_slab[0], L.slab_stride, NCCL_UINT8, ctx->nccl_comm, ctx->stream);
+        if (nrc != 0) { nccl_fail(op, "ncclAllGather(winner slabs)", nrc); return; }
+    } else {
+        wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(mine + flag_off(1, op.b, 0)), x->nranks, op.epoch, x->scratch + 8);
+        KX_LAUNCHED(ctx);
+    }
+    MergeParams M;
+    memset(&M, 0, sizeof M);
+    M.slabs = mine + L.o_slab[op.b]; M.stride = L.slab_stride; M.R = x->nranks;
+    M.slab_rows_cap = op.nccl ? x->scaps.rows : x->caps.rows;
+    M.a = reinterpret_cast<const unsigned long long *>(mine + L.o_a[op.b]);
+    M.tab = t->dev; M.row_key = t->row_key; M.row_name_off = t->row_name_off; M.row_name_len = t->row_name_len;
+    M.row_line = t->row_line; M.row_anchor = t->row_anchor; M.blob = t->blob; M.rows_cap = t->rows_cap; M.blob_cap = t->blob_cap;
+    M.timeout_flag = x->scratch + 8;
+    merge_kernel<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(M);
+    KX_LAUNCHED(ctx);
+    if (ctx->stage_timing) { cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE + 1], ctx->stream); ctx->ev_used[KXPU_T_MERGE] = true; }
+    if (op.a.nq_total == 0) return;
+    KxTimer tm(ctx, KXPU_T_LOOKUP);
+    if (op.nccl) {
+        // probe straight into my slice of the caller's buffer; the all-gather of hits follows in phase 4
+        if (op.a.nq) op.rc = kx_launch_lookup(ctx, t, op.a.d_keys, op.a.nq, op.a.d_rows_all + op.a.key_offset);
+        return;
+    }
+    JoinParams J;
+    memset(&J, 0, sizeof J);
+    J.keys = op.a.d_keys; J.n = op.a.nq; J.key_offset = op.a.key_offset; J.slots = t->dev.slots; J.cap = t->cap; J.shift = t->shift;
+    J.tg = targets(op); J.o_res = L.o_res[op.b]; J.o_flag = flag_off(2, op.b, x->rank); J.raise_flags = 1; J.epoch = op.epoch;
+    J.done = x->scratch + 2;
+    size_t blocks = std::max<size_t>((op.a.nq + 255) / 256, 1);
+    blocks = std::min<size_t>(blocks, (size_t)ctx->sm_count * 16);
+    join_gather_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(J);
+    KX_LAUNCHED(ctx);
+}
+
+// phase 4: everybody's hits have landed -> caller's buffer; counters to the host
+static void shard_phase4(ShardOp &op) {
+    if (op.rc != KXPU_OK) return;
+    kxpu_ctx *ctx = op.ctx;
+    KxExchange *x = op.x;
+    const XLayout &L = layout(op);
+    uint8_t *mine = my_region(op);
+    if (op.a.nq_total) {
+        if (op.nccl) {
+            const int nrc = g_nccl.all_gather(op.a.d_rows_all + op.a.key_offset, op.a.d_rows_all, op.a.nq * 4, NCCL_UINT8, ctx->nccl_comm, ctx->stream);
+            if (nrc != 0) { nccl_fail(op, "ncclAllGather(hits)", nrc); return; }
+        } else {
+            wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(mine + flag_off(2, op.b, 0)), x->nranks, op.epoch, x->scratch + 8);
+            KX_LAUNCHED(ctx);
+            if (op.a.d_rows_all)
+                cudaMemcpyAsync(op.a.d_rows_all, mine + L.o_res[op.b], op.a.nq_total * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        }
+    }
+    cudaMemcpyAsync(ctx->h_ctl, op.t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (!op.nccl) cudaMemcpyAsync(ctx->h_ctl + 32, x->scratch + 8, 4, cudaMemcpyDeviceToHost, ctx->stream);
+}
+
+enum { SH_DONE = 0, SH_RETRY = 1, SH_FAIL = 2 };
+
+// The one host round trip of the load.  Every rank reads the same summary and decides alike.
+static int shard_complete(ShardOp &op, kxpu_table **out, int32_t *rc_out) {
+    kxpu_ctx *ctx = op.ctx;
+    KxExchange *x = op.x;
+    auto fail = [&](int32_t rc) {
+        if (op.t) { kx_table_release(ctx, op.t); op.t = nullptr; }
+        *rc_out = rc;
+        return (int)SH_FAIL;
+    };
+    if (op.rc != KXPU_OK) {
+        // an enqueue phase failed on this rank only: the peers are waiting for pushes that never
+        // come and will time out -- the exchange cannot be used any more
+        if (op.rc != KXPU_E_INVALID && op.rc != KXPU_E_UNSUPPORTED) x->broken = true;
+        else if (x->nranks > 1) x->broken = true;
+        cudaStreamSynchronize(ctx->stream);
+        return fail(op.rc);
+    }
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        KX_SET_ERR(ctx, "sharded load failed: %s", cudaGetErrorString(e));
+        x->broken = true;
+        return fail(KXPU_E_CUDA);
+    }
+    const uint32_t *h = ctx->h_ctl;
+    const uint32_t st = h[KX_C_XSTATUS];
+    if ((st & 0x80000000u) || (!op.nccl && h[32])) {
+        KX_SET_ERR(ctx, "peer-memory exchange: a rank did not deliver within 4 s (epoch %u)", op.epoch);
+        x->broken = true;
+        cudaMemsetAsync(x->scratch + 8, 0, 4, ctx->stream);
+        return fail(KXPU_E_NCCL);
+    }
+    kxpu_table *t = op.t;
+    const uint32_t total_rows = h[KX_C_XROWS], total_blob = h[KX_C_XBLOB], maxkeys = h[KX_C_XMAXKEYS];
+    const bool grow_cap = (st & XS_GROW) || total_rows + maxkeys > t->dev.max_keys || total_rows > t->rows_cap;
+    const bool grow_blob = (st & XS_GROW_BLOB) || total_blob > t->blob_cap;
+    const bool need_trunc = (st & XS_NEED_TRUNC) != 0;
+    const bool slab_over = (st & XS_SLAB_OVERFLOW) != 0;
+    if (grow_cap || grow_blob || need_trunc || slab_over) {
+        kx_table_release(ctx, t);
+        op.t = nullptr;
+        if (grow_cap) {
+            uint32_t cap = x->x_cap;
+            if (!kx_grow_cap(&cap, (size_t)op.a.n * (size_t)x->nranks)) { *rc_out = KXPU_E_CAPACITY; return SH_FAIL; }
+            x->x_cap = cap;
+        }
+        if (grow_blob) {
+            if (x->x_blob_cap >= (1u << 31)) { *rc_out = KXPU_E_CAPACITY; return SH_FAIL; }
+            x->x_blob_cap <<= 2;
+        }
+        if (need_trunc) op.have_trunc = true;
+        if (slab_over) {
+            if (op.nccl) { x->scaps.rows = std::max<uint32_t>(x->scaps.rows, 65536u) << 2; x->scaps.blob = std::max<uint32_t>(x->scaps.blob, 2u << 20) << 2; }
+            else if (ctx->multi) { KX_SET_ERR(ctx, "winner rows outgrow the peer slab (%u rows / %u name bytes per rank)", x->caps.rows, x->caps.blob); *rc_out = KXPU_E_CAPACITY; return SH_FAIL; }
+            else x->use_nccl = true;  // the fixed peer slab is too small for this text: NCCL transport with a growing slab
+        }
+        return SH_RETRY;
+    }
+    if (h[KX_C_OVERFLOW]) { kx_table_release(ctx, t); op.t = nullptr; *rc_out = KXPU_E_CAPACITY; return SH_FAIL; }  // unreachable: covered by grow_cap
+    t->n_rows = total_rows;
+    t->blob_used = total_blob;
+    *out = t;
+    op.t = nullptr;
+    *rc_out = KXPU_OK;
+    return SH_DONE;
+}
+
+static int32_t shard_run(kxpu_ctx *ctx, const ShardArgs &a, kxpu_table **out) {
+    KxExchange *x = ctx->xch;
+    ShardOp op;
+    op.ctx = ctx; op.x = x; op.a = a;
+    for (int attempt = 0; attempt < 16; attempt++) {
+        shard_phase1(op);
+        shard_phase2(op);
+        shard_phase3(op);
+        shard_phase4(op);
+        int32_t rc = KXPU_OK;
+        const int r = shard_complete(op, out, &rc);
+        if (r == SH_DONE) return KXPU_OK;
+        if (r == SH_FAIL) return rc;
+    }
+    return KXPU_E_CAPACITY;
+}
+
+}  // namespace kxx
+
+using namespace kxx;
+
+void kx_exchange_destroy(kxpu_ctx *ctx) { exchange_free(ctx); }
+
+// ------------------------------------------------------------------ ABI: one process per rank
 extern "C" int32_t kxpu_comm_unique_id(uint8_t id_out[KXPU_COMM_ID_BYTES]) {
     if (!id_out) return KXPU_E_INVALID;
     if (!nccl_load()) return KXPU_E_NCCL;
@@ -123,22 +777,25 @@ extern "C" int32_t kxpu_comm_init(kxpu_ctx *ctx, int32_t nranks, int32_t rank, c
     if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return KXPU_E_INVALID;
     std::lock_guard<std::mutex> guard(ctx->mu);
     cudaSetDevice(ctx->device);
+    if (ctx->multi || ctx->nccl_comm || ctx->xch) return KXPU_E_INVALID;
     if (!nccl_load()) { KX_SET_ERR(ctx, "libnccl.so.2 not found"); return KXPU_E_NCCL; }
-    if (ctx->nccl_comm) return KXPU_E_INVALID;
     UniqueId uid;
     memcpy(uid.internal, id, 128);
     void *comm = nullptr;
-    int rc = ((fn_comm_init_rank_byval)g_nccl.comm_init_rank)(&comm, nranks, uid, rank);
+    const int rc = g_nccl.comm_init_rank(&comm, nranks, uid, rank);
     if (rc != 0) {
         KX_SET_ERR(ctx, "ncclCommInitRank: %s", g_nccl.err_string ? g_nccl.err_string(rc) : "error");
         return KXPU_E_NCCL;
     }
+    KxExchange *x = new (std::nothrow) KxExchange();
+    if (!x) { g_nccl.comm_destroy(comm); return KXPU_E_NOMEM; }
     ctx->nccl_comm = comm;
     ctx->nranks = nranks;
     ctx->rank = rank;
-    p2p_setup(ctx, [&](const void *src, void *dst, size_t nbytes) {
-        return g_nccl.all_gather(src, dst, nbytes, /*ncclUint8*/ 1, ctx->nccl_comm, ctx->stream);
-    });
+    x->nranks = nranks;
+    x->rank = rank;
+    ctx->xch = x;
+    ipc_setup(ctx, x);
     return KXPU_OK;
 }
 
@@ -146,150 +803,206 @@ extern "C" int32_t kxpu_comm_destroy(kxpu_ctx *ctx) {
     if (!ctx) return KXPU_E_INVALID;
     std::lock_guard<std::mutex> guard(ctx->mu);
     cudaSetDevice(ctx->device);
+    if (ctx->multi) return KXPU_E_INVALID;
+    cudaStreamSynchronize(ctx->stream);
+    exchange_free(ctx);
     if (ctx->nccl_comm) {
-        cudaStreamSynchronize(ctx->stream);
-        p2p_teardown(ctx);
         g_nccl.comm_destroy(ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
-        ctx->nranks = 1;
-        ctx->rank = 0;
+    }
+    ctx->nranks = 1;
+    ctx->rank = 0;
+    return KXPU_OK;
+}
+
+static int32_t check_shard_args(kxpu_ctx *ctx, const ShardArgs &a, kxpu_table **out) {
+    if (!out || (!a.d_text && a.n)) return KXPU_E_INVALID;
+    if (a.nq_total) {
+        if ((a.nq && !a.d_keys) || a.key_offset + a.nq > a.nq_total) return KXPU_E_INVALID;
+        KxExchange *x = ctx->xch;
+        if (x && x->p2p && !x->use_nccl && a.nq_total > x->caps.join) {
+            KX_SET_ERR(ctx, "sharded join of %zu keys exceeds the exchange capacity of %u", a.nq_total, x->caps.join);
+            return KXPU_E_UNSUPPORTED;
+        }
+        if (x && (!x->p2p || x->use_nccl) && (!a.d_rows_all || a.key_offset != (size_t)x->rank * a.nq || a.nq * (size_t)x->nranks != a.nq_total)) {
+            KX_SET_ERR(ctx, "NCCL transport needs equal key slices in rank order and a result buffer");
+            return KXPU_E_UNSUPPORTED;
+        }
     }
     return KXPU_OK;
 }
 
-extern "C" int32_t kxpu_pciids_load_sharded(kxpu_ctx *ctx, const void *d_text_shard, size_t n, uint64_t global_base,
-                                            kxpu_table **out) {
-    if (!ctx || !out || (!d_text_shard && n)) return KXPU_E_INVALID;
+extern "C" int32_t kxpu_pciids_join_sharded(kxpu_ctx *ctx, const void *d_text_shard, size_t n, uint64_t global_base,
+                                            const uint32_t *d_keys, size_t nq, size_t key_offset, size_t nq_total,
+                                            int32_t *d_rows_all, kxpu_table **out) {
+    if (!ctx) return KXPU_E_INVALID;
     std::lock_guard<std::mutex> guard(ctx->mu);
     cudaSetDevice(ctx->device);
     kx_clear_timings(ctx);
-    if (!ctx->nccl_comm) { KX_SET_ERR(ctx, "kxpu_comm_init has not been called"); return KXPU_E_NCCL; }
-    const int R = ctx->nranks;
-
-    // 1. local parse: every candidate row of the shard (validity is a global property)
-    kxpu_table *local = nullptr;
-    int32_t rc = kx_build_table(ctx, (const uint8_t *)d_text_shard, n, global_base, 0, 0, &local);
+    if (ctx->multi) { KX_SET_ERR(ctx, "this ctx belongs to a kxpu_multi group: use kxpu_multi_pciids_join"); return KXPU_E_INVALID; }
+    if (!ctx->xch) { KX_SET_ERR(ctx, "kxpu_comm_init has not been called"); return KXPU_E_NCCL; }
+    ShardArgs a{(const uint8_t *)d_text_shard, n, global_base, d_keys, nq, key_offset, nq_total, d_rows_all};
+    const int32_t rc = check_shard_args(ctx, a, out);
     if (rc != KXPU_OK) return rc;
-    KxTableDev dev;
-    uint32_t cap, n_rows, blob_used;
-    const uint32_t *row_key, *row_name_off, *row_name_len;
-    const unsigned long long *row_line, *row_anchor;
-    const uint8_t *blob;
-    kx_table_local_view(local, &dev, &cap, &n_rows, &blob_used, &row_key, &row_line, &row_anchor, &row_name_off,
-                        &row_name_len, &blob);
+    return shard_run(ctx, a, out);
+}
 
-    // ---- peer-memory path: pack into my slot, push it to every peer, wait for everybody's flag, merge
-    if (ctx->p2p_ok) {
-        const SlabCaps caps = kDefaultCaps;
-        const uint32_t e = ++ctx->p2p_epoch;
-        const int b = (int)(e & 1u);
-        const size_t slot0 = P2P_FLAGS_BYTES + (size_t)b * (size_t)R * ctx->p2p_stride;
-        if (ctx->stage_timing) cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE], ctx->stream);
-        static const bool ptrace = getenv("KXPU_TRACE_MERGE") != nullptr;
-        static cudaEvent_t pev[4];
-        static bool pev_ok = false;
-        if (ptrace && !pev_ok) { for (auto &e2 : pev) cudaEventCreate(&e2); pev_ok = true; }
-        if (ptrace) cudaEventRecord(pev[0], ctx->stream);
-        PushParams PP;
-        memset(&PP, 0, sizeof PP);
-        PP.nranks = R; PP.epoch = e; PP.caps = caps; PP.scratch = ctx->p2p_scratch;
-        PP.n_rows = n_rows; PP.blob_used = blob_used; PP.row_key = row_key; PP.row_name_off = row_name_off;
-        PP.row_name_len = row_name_len; PP.row_line = row_line; PP.row_anchor = row_anchor; PP.trunc = dev.trunc;
-        PP.vendor_first = dev.vendor_first; PP.blob = blob;
-        for (int q = 0; q < R; q++) {
-            PP.dst[q] = ctx->p2p_peer[q] + slot0 + (size_t)ctx->rank * ctx->p2p_stride;
-            PP.flag[q] = reinterpret_cast<uint32_t *>(ctx->p2p_peer[q]) + b * kxpu_ctx::KX_P2P_MAX_RANKS + ctx->rank;
-        }
-        pack_push_kernel<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(PP);
-        if (ptrace) cudaEventRecord(pev[1], ctx->stream);
-        wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(ctx->p2p_local) + b * kxpu_ctx::KX_P2P_MAX_RANKS,
-                                                     R, e, ctx->p2p_scratch + 1);
-        ctx->launches += 2;
-        if (ptrace) cudaEventRecord(pev[2], ctx->stream);
-        kxpu_table *merged = nullptr;
-        rc = kx_table_from_gather(ctx, ctx->p2p_local + slot0, R, ctx->p2p_stride, caps, &merged, /*own_names=*/true, ctx->p2p_scratch + 1);
-        if (ptrace) {
-            cudaEventRecord(pev[3], ctx->stream);
-            cudaEventSynchronize(pev[3]);
-            float a = 0, b2 = 0, c2 = 0;
-            cudaEventElapsedTime(&a, pev[0], pev[1]); cudaEventElapsedTime(&b2, pev[1], pev[2]); cudaEventElapsedTime(&c2, pev[2], pev[3]);
-            static int calls = 0;
-            if (++calls % 8 == 0) fprintf(stderr, "[kxpu merge trace] pack+push %.1f us  wait %.1f us  merge+sync %.1f us  (peer memory, %d ranks)\n", a * 1e3, b2 * 1e3, c2 * 1e3, R);
-        }
-        if (ctx->stage_timing) { cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE + 1], ctx->stream); ctx->ev_used[KXPU_T_MERGE] = true; }
-        if (rc == KXPU_E_NCCL) {  // a peer never delivered (flagged by the wait kernel, seen by the merge)
-            cudaMemsetAsync(ctx->p2p_scratch, 0, 256, ctx->stream);
-            kx_table_release(ctx, local);
-            return rc;
-        }
-        if (rc != KXPU_E_CAPACITY) {  // a slab outgrew the fixed exchange region: every rank falls back to NCCL below
-            kx_table_release(ctx, local);
-            if (rc != KXPU_OK) return rc;
-            *out = merged;
-            return KXPU_OK;
+extern "C" int32_t kxpu_pciids_load_sharded(kxpu_ctx *ctx, const void *d_text_shard, size_t n, uint64_t global_base,
+                                            kxpu_table **out) {
+    return kxpu_pciids_join_sharded(ctx, d_text_shard, n, global_base, nullptr, 0, 0, 0, nullptr, out);
+}
+
+// ------------------------------------------------------------------ ABI: one process, N GPUs
+struct kxpu_multi {
+    int n = 0;
+    kxpu_ctx *ctx[KX_MAX_RANKS] = {};
+};
+
+int32_t kx_ctx_create_on(int32_t ordinal, kxpu_ctx **out);  // api.cu
+
+extern "C" int32_t kxpu_multi_destroy(kxpu_multi *m) {
+    if (!m) return KXPU_E_INVALID;
+    for (int i = 0; i < m->n; i++) {
+        if (!m->ctx[i]) continue;
+        cudaSetDevice(m->ctx[i]->device);
+        cudaStreamSynchronize(m->ctx[i]->stream);
+    }
+    for (int i = 0; i < m->n; i++) {
+        if (!m->ctx[i]) continue;
+        m->ctx[i]->multi = nullptr;
+        kxpu_ctx_destroy(m->ctx[i]);
+    }
+    delete m;
+    return KXPU_OK;
+}
+
+extern "C" int32_t kxpu_ctx_create_multi(const int32_t *ordinals, int32_t n, kxpu_multi **out) {
+    if (!ordinals || !out || n < 1 || n > KX_MAX_RANKS) return KXPU_E_INVALID;
+    *out = nullptr;
+    kxpu_multi *m = new (std::nothrow) kxpu_multi();
+    if (!m) return KXPU_E_NOMEM;
+    m->n = n;
+    int32_t rc = KXPU_OK;
+    for (int i = 0; i < n && rc == KXPU_OK; i++) rc = kx_ctx_create_on(ordinals[i], &m->ctx[i]);
+    // every pair of distinct devices needs peer access in both directions (NVSwitch: always there)
+    for (int i = 0; i < n && rc == KXPU_OK; i++) {
+        cudaSetDevice(m->ctx[i]->device);
+        for (int j = 0; j < n && rc == KXPU_OK; j++) {
+            if (m->ctx[j]->device == m->ctx[i]->device) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, m->ctx[i]->device, m->ctx[j]->device);
+            if (!can) { rc = KXPU_E_NCCL; break; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(m->ctx[j]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = KXPU_E_CUDA;
+            cudaGetLastError();
         }
     }
-
-    SlabCaps caps{32768u, 8192u, 1u << 20};
-    if (ctx->p2p_ok) { caps.rows *= 4; caps.vendors = 65536; caps.blob *= 8; }  // the default capacities just overflowed
-    for (int attempt = 0; attempt < 6; attempt++) {
-        const size_t sb = (slab_bytes(caps) + 255) / 256 * 256;
-        uint8_t *d_slab = nullptr, *d_gather = nullptr;
-        cudaError_t e = cudaMallocAsync((void **)&d_slab, sb, ctx->stream);
-        if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_gather, sb * (size_t)R, ctx->stream);
-        if (e != cudaSuccess) {
-            KX_SET_ERR(ctx, "gather buffers: %s", cudaGetErrorString(e));
-            kx_table_release(ctx, local);
-            return KXPU_E_NOMEM;
+    for (int i = 0; i < n && rc == KXPU_OK; i++) {
+        kxpu_ctx *c = m->ctx[i];
+        cudaSetDevice(c->device);
+        KxExchange *x = new (std::nothrow) KxExchange();
+        if (!x) { rc = KXPU_E_NOMEM; break; }
+        x->nranks = n; x->rank = i;
+        c->xch = x; c->nranks = n; c->rank = i;
+        rc = region_alloc(c, x, kPeerCaps);
+    }
+    if (rc == KXPU_OK) {
+        for (int i = 0; i < n; i++) {
+            KxExchange *x = m->ctx[i]->xch;
+            for (int j = 0; j < n; j++) x->peer[j] = m->ctx[j]->xch->local;  // direct pointers: one address space
+            x->p2p = true;
+            x->ipc = false;
         }
-        if (ctx->stage_timing) cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE], ctx->stream);
-        static const bool trace = getenv("KXPU_TRACE_MERGE") != nullptr;
-        static cudaEvent_t tev[4];
-        static bool tev_ok = false;
-        if (trace && !tev_ok) { for (auto &e2 : tev) cudaEventCreate(&e2); tev_ok = true; }
-        if (trace) cudaEventRecord(tev[0], ctx->stream);
-        // 2. pack the slab
-        cudaMemsetAsync(d_slab, 0, sizeof(SlabHeader), ctx->stream);
-        pack_rows_kernel<<<(std::max(n_rows, 1u) + 255) / 256, 256, 0, ctx->stream>>>(
-            d_slab, caps, n_rows, row_key, row_line, row_anchor, row_name_off, row_name_len, dev.trunc, blob_used);
-        pack_vendors_kernel<<<65536 / 256, 256, 0, ctx->stream>>>(d_slab, caps, dev.vendor_first);
-        ctx->launches += 2;
-        if (blob_used > 0 && blob_used <= caps.blob)
-            cudaMemcpyAsync(d_slab + slab_blob_off(caps), blob, blob_used, cudaMemcpyDeviceToDevice, ctx->stream);
-        if (trace) cudaEventRecord(tev[1], ctx->stream);
-        // 3. the one collective of the path
-        int nrc = g_nccl.all_gather(d_slab, d_gather, sb, /*ncclUint8*/ 1, ctx->nccl_comm, ctx->stream);
-        if (nrc != 0) {
-            KX_SET_ERR(ctx, "ncclAllGather: %s", g_nccl.err_string ? g_nccl.err_string(nrc) : "error");
-            cudaFreeAsync(d_slab, ctx->stream);
-            cudaFreeAsync(d_gather, ctx->stream);
-            kx_table_release(ctx, local);
-            return KXPU_E_NCCL;
-        }
-        if (trace) cudaEventRecord(tev[2], ctx->stream);
-        cudaFreeAsync(d_slab, ctx->stream);
-        // 4. min-merge into a fresh table (keeps d_gather: the names live there)
-        kxpu_table *merged = nullptr;
-        rc = kx_table_from_gather(ctx, d_gather, R, sb, caps, &merged, /*own_names=*/false, nullptr);
-        if (ctx->stage_timing) { cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE + 1], ctx->stream); ctx->ev_used[KXPU_T_MERGE] = true; }
-        if (trace) {
-            cudaEventRecord(tev[3], ctx->stream);
-            cudaEventSynchronize(tev[3]);
-            float a = 0, b = 0, c2 = 0;
-            cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]); cudaEventElapsedTime(&c2, tev[2], tev[3]);
-            static int calls = 0;
-            if (++calls % 8 == 0) fprintf(stderr, "[kxpu merge trace] pack %.1f us  all-gather %.1f us  merge+sync %.1f us  slab %zu B x %d\n", a * 1e3, b * 1e3, c2 * 1e3, sb, R);
-        }
-        if (rc == KXPU_E_CAPACITY) {
-            // some rank overflowed a slab capacity: every rank sees the same headers and retries alike
-            caps.rows *= 4; caps.vendors = 65536; caps.blob *= 8;
-            continue;
-        }
-        kx_table_release(ctx, local);
-        if (rc != KXPU_OK) return rc;
-        *out = merged;
+        for (int i = 0; i < n; i++) m->ctx[i]->multi = m;
+        *out = m;
         return KXPU_OK;
     }
-    kx_table_release(ctx, local);
-    return KXPU_E_CAPACITY;
+    kxpu_multi_destroy(m);
+    return rc;
+}
+
+extern "C" int32_t kxpu_multi_size(kxpu_multi *m) { return m ? m->n : 0; }
+extern "C" kxpu_ctx *kxpu_multi_ctx(kxpu_multi *m, int32_t i) { return (m && i >= 0 && i < m->n) ? m->ctx[i] : nullptr; }
+
+extern "C" int32_t kxpu_multi_pciids_join(kxpu_multi *m, const kxpu_shard *shards, size_t nq_total, kxpu_table **tables_out) {
+    if (!m || !shards || !tables_out) return KXPU_E_INVALID;
+    const int n = m->n;
+    // all ranks are driven from this thread, phase by phase: when a rank's wait is enqueued, the push
+    // it waits for is already in its peer's stream, so the host never blocks in front of a wait
+    for (int i = 0; i < n; i++) m->ctx[i]->mu.lock();
+    ShardOp ops[KX_MAX_RANKS];
+    int32_t rc = KXPU_OK;
+    for (int i = 0; i < n; i++) {
+        kxpu_ctx *c = m->ctx[i];
+        tables_out[i] = nullptr;
+        kx_clear_timings(c);
+        ops[i].ctx = c; ops[i].x = c->xch;
+        ops[i].a = ShardArgs{(const uint8_t *)shards[i].d_text, shards[i].n, shards[i].global_base, shards[i].d_keys, shards[i].nq,
+                            shards[i].key_offset, nq_total, shards[i].d_rows_all};
+        cudaSetDevice(c->device);
+        const int32_t r = check_shard_args(c, ops[i].a, &tables_out[i]);
+        if (r != KXPU_OK && rc == KXPU_OK) rc = r;
+    }
+    for (int attempt = 0; attempt < 16 && rc == KXPU_OK; attempt++) {
+        for (int ph = 1; ph <= 4; ph++) {
+            for (int i = 0; i < n; i++) {
+                cudaSetDevice(ops[i].ctx->device);
+                if (ph == 1) shard_phase1(ops[i]);
+                else if (ph == 2) shard_phase2(ops[i]);
+                else if (ph == 3) shard_phase3(ops[i]);
+                else shard_phase4(ops[i]);
+            }
+        }
+        bool retry = false, done = true;
+        for (int i = 0; i < n; i++) {
+            cudaSetDevice(ops[i].ctx->device);
+            int32_t r = KXPU_OK;
+            const int s = shard_complete(ops[i], &tables_out[i], &r);
+            if (s == SH_RETRY) { retry = true; done = false; }
+            else if (s == SH_FAIL) { if (rc == KXPU_OK) rc = r; done = false; }
+        }
+        if (rc != KXPU_OK) break;
+        if (done) break;
+        if (!retry) break;
+        for (int i = 0; i < n; i++)  // a retry is collective: ranks that finished hand their table back
+            if (tables_out[i]) { cudaSetDevice(ops[i].ctx->device); kx_table_release(ops[i].ctx, tables_out[i]); tables_out[i] = nullptr; }
+    }
+    if (rc != KXPU_OK)
+        for (int i = 0; i < n; i++)
+            if (tables_out[i]) { cudaSetDevice(ops[i].ctx->device); kx_table_release(ops[i].ctx, tables_out[i]); tables_out[i] = nullptr; }
+    for (int i = n - 1; i >= 0; i--) m->ctx[i]->mu.unlock();
+    return rc;
+}
+
+// ------------------------------------------------------------------ shard planning (host)
+// Smallest offset >= pos at which a top-level line starts (n if none): a line start whose first
+// byte is neither '\t' nor '#'.
+static size_t next_top_level_start(const uint8_t *text, size_t n, size_t pos) {
+    if (pos == 0) return 0;
+    if (pos >= n) return n;
+    size_t p = pos;
+    if (text[p - 1] != '\n') {
+        const void *nl = memchr(text + p, '\n', n - p);
+        if (!nl) return n;
+        p = (size_t)((const uint8_t *)nl - text) + 1;
+    }
+    while (p < n) {
+        if (text[p] != '\t' && text[p] != '#') return p;
+        const void *nl = memchr(text + p, '\n', n - p);
+        if (!nl) return n;
+        p = (size_t)((const uint8_t *)nl - text) + 1;
+    }
+    return n;
+}
+
+extern "C" int32_t kxpu_plan_shards(const uint8_t *text, size_t n, int32_t nranks, uint64_t *cuts_out) {
+    if ((!text && n) || nranks < 1 || !cuts_out) return KXPU_E_INVALID;
+    cuts_out[0] = 0;
+    for (int r = 1; r < nranks; r++) {
+        const size_t want = (size_t)((unsigned __int128)n * (unsigned)r / (unsigned)nranks);
+        const size_t c = next_top_level_start(text, n, want);
+        cuts_out[r] = std::max<uint64_t>(cuts_out[r - 1], c);
+    }
+    cuts_out[nranks] = n;
+    return KXPU_OK;
 }

@@ -6,8 +6,22 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "../../include/kxpu.h"
+
+constexpr int KX_MAX_RANKS = 16;  // ranks of one sharded load (one NVSwitch domain)
+
+
+struct KxArena {  // one pooled table arena (api.cu): reset on release, handed out clean
+    void *p = nullptr;
+    size_t bytes = 0;
+    uint32_t cap = 0, blob_cap = 0;
+    size_t range_bytes = 0;
+};
+
+struct KxExchange;  // comm.cu: peer-memory exchange state of a sharded load
+struct kxpu_multi;
 
 struct kxpu_ctx {
     int device = -1;
@@ -23,19 +37,22 @@ struct kxpu_ctx {
     char err[512] = {0};
     // pinned staging for small H2D/D2H control words
     uint32_t *h_ctl = nullptr;  // 64 words, pinned
-    // NCCL (lazy)
+    // table arenas: released tables park their (already reset) arena here
+    std::vector<KxArena> pool;
+    uint32_t cap_hint = 1u << 16;       // table capacity the next load starts with (follows the last text)
+    uint32_t blob_hint = 0;             // name blob capacity of the last load (0 = derive from the text size)
+    // tile status words of the single-pass scans / look-backs (scan.cuh): zeroed once, epoch-tagged
+    unsigned long long *scan_state = nullptr;
+    size_t scan_state_words = 0;
+    uint32_t scan_epoch = 0;
+    // host staging of kxpu_pciids_load / kxpu_lookup (grown on demand, kept)
+    void *d_stage = nullptr;
+    size_t d_stage_bytes = 0;
+    // NCCL (lazy) and the exchange of the sharded load (comm.cu)
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;
-    // peer-memory exchange of the sharded load (comm.cu): this rank's region and the peers' regions
-    // mapped through CUDA IPC; layout [flags u32[2][16] | pad to 256 | slab[2][nranks]]
-    static constexpr int KX_P2P_MAX_RANKS = 16;
-    uint8_t *p2p_local = nullptr;
-    uint8_t *p2p_peer[KX_P2P_MAX_RANKS] = {};
-    size_t p2p_stride = 0;
-    uint32_t p2p_epoch = 0;
-    uint32_t *p2p_scratch = nullptr;  // device: [0] push-done counter, [1] wait timeout flag
-    bool p2p_ok = false;
-    int parse_version = 2;
+    KxExchange *xch = nullptr;
+    kxpu_multi *multi = nullptr;  // set when the ctx belongs to a kxpu_ctx_create_multi group
 };
 
 #define KX_SET_ERR(ctx, ...) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__)
@@ -67,26 +84,30 @@ struct KxTimer {  // records a CUDA-event pair around a stage on the ctx stream
 
 static inline void kx_clear_timings(kxpu_ctx *c) { memset(c->ev_used, 0, sizeof(c->ev_used)); }
 
+// >= `words` zero-initialised-once status words for look-backs (nullptr on allocation failure) and
+// the epoch of the next look-back (api.cu)
+unsigned long long *kx_scan_state(kxpu_ctx *ctx, size_t words);
+uint32_t kx_next_epoch(kxpu_ctx *ctx);
+
+// stream-ordered scratch that is released on every path out of a call
+struct KxScratch {
+    kxpu_ctx *c;
+    std::vector<void *> ptrs;
+    explicit KxScratch(kxpu_ctx *ctx) : c(ctx) {}
+    cudaError_t alloc(void **p, size_t bytes) {
+        cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, c->stream);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        else *p = nullptr;
+        return e;
+    }
+    ~KxScratch() {
+        for (void *p : ptrs) cudaFreeAsync(p, c->stream);
+    }
+};
+
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t kx_lane() { return threadIdx.x & 31u; }
-
-// Parse four ASCII bytes (first character in the low byte) as lowercase hex.
-// Only [0-9a-f] is accepted: sysfs ids are lowercase, and the reference compares raw
-// bytes (strings.HasPrefix, device_plugin.go:237,265).
-__device__ __forceinline__ bool kx_hex4(uint32_t w, uint32_t &v) {
-    uint32_t acc = 0, bad = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t c = (w >> (8 * i)) & 0xffu;
-        uint32_t d = c - 0x30u, a = c - 0x61u;
-        uint32_t x = d < 10u ? d : a + 10u;
-        bad |= (d >= 10u) & (a >= 6u);
-        acc = (acc << 4) | (x & 15u);
-    }
-    v = acc;
-    return bad == 0;
-}
 
 __device__ __forceinline__ uint32_t kx_hash(uint32_t key) { return key * 0x9E3779B1u; }
 #endif

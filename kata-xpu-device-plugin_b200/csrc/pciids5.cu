@@ -1,9 +1,9 @@
-// pciids5.cu -- parse kernel v5 (default): warp-autonomous, alive-first, nothing waits.
+// pciids5.cu -- the pci.ids parse kernel: warp-autonomous, alive-first, nothing waits.
 //
-// v4 (pciids4.cu) showed where the rest of the time went once dead blocks were skipped
-// (profiles/r01_parse_v4d_*): 8 % of all instructions were warps polling the CTA barrier that
-// orders the per-chunk status words, and the per-iteration bookkeeping of the shared ticket /
-// phase-B pipeline cost as much as the newline masks.  v5 removes the sharing:
+// Replaces the per-key file scan of getDeviceName / locateVendor (reference
+// pkg/device_plugin/device_plugin.go:208-275): the text is streamed through shared memory ONCE
+// and every (vendor,device) pair is folded into a hash table with "first occurrence wins"
+// semantics; lookups are then O(1) probes.
 //   * the text is cut into RANGES of 8 chunks (16 KiB; fewer for texts too small to give every
 //     warp of the grid a range) handed out to WARPS by ticket (a static
 //     split leaves the SM half empty at the end: the issue arbiter favours some warps, they
@@ -17,27 +17,18 @@
 //     keeps in two registers along its range; at the start of a range the carry is not known
 //     (the range before belongs to another warp): the warp only counts how many leading chunks
 //     are affected (one word per range);
-//   * resolve_ranges_kernel: one thread per range walks back over the per-range status words
-//     (all published by then); only if the governing line is alive -- the first copy of a
-//     vendor block -- the leading chunks are queued, and resolve_chunks_kernel stages each of
-//     them again (one warp per chunk) and folds its head lines.
-// Results are exactly those of v1..v4 (same fold rule, same finalize).
+//   * resolve_ranges_kernel: one lane per range looks back over the per-range status words
+//     (all published by then), 32 ranges per step; only if the governing line is alive -- the
+//     first copy of a vendor block -- the leading chunks are queued, and resolve_chunks_kernel
+//     stages each of them again (one warp per chunk) and folds its head lines.
+// Earlier generations (CTA-tiled, per-chunk look-back, super-chunks, CTA barrier per 16 KiB) are
+// in the git history and in profiles/r01_parse_v*; DESIGN.md has the numbers.
 #pragma once
-#include "common.cuh"
-#include "pciids4.cu"  // shared-window helpers, chunk_masks, fold_lines, stage_chunk_manual
-#include "table.cuh"
+#include "parse_common.cuh"
 
 namespace kxparse5 {
 
-using namespace kxparse2;
-using kxparse4::chunk_masks;
-using kxparse4::fold_lines;
-using kxparse4::lds32_unaligned;
-using kxparse4::lds8;
-using kxparse4::mbar_expect_tx_a;
-using kxparse4::mbar_try_a;
-using kxparse4::stage_chunk_manual;
-using kxparse4::tma_load_a;
+using namespace kxparse;
 
 constexpr int STAGES5 = 3;
 constexpr int RCH5_MAX = 8;  // chunks per range (16 KiB); fewer for small texts so that every warp gets a range
@@ -64,7 +55,7 @@ struct Params5 {
 };
 
 
-// Newline masks of the chunk staged at shared address st (see kxparse4::chunk_masks for the
+// Newline masks of the chunk staged at shared address st (see kxparse::chunk_masks for the
 // window layout): nl[h] bit b = a line starts after the newline at byte b of the lane's window in
 // KiB half h, trimmed to real line starts (< n_rel).
 __device__ __forceinline__ void nl_masks(uint32_t st, uint32_t lane, uint32_t n_rel, uint32_t k7f, uint32_t k0a, uint32_t k80,
@@ -74,8 +65,8 @@ __device__ __forceinline__ void nl_masks(uint32_t st, uint32_t lane, uint32_t n_
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const uint32_t o = (uint32_t)h * HALF + lane * 32u;
-        const uint4 va = kxparse4::lds128(st + o + 16u * swz);
-        const uint4 vb = kxparse4::lds128(st + o + 16u * (swz ^ 1u));
+        const uint4 va = lds128(st + o + 16u * swz);
+        const uint4 vb = lds128(st + o + 16u * (swz ^ 1u));
         const uint32_t ma = nl_mask16(va, k7f, k0a, k80), mb = nl_mask16(vb, k7f, k0a, k80);
         const uint32_t m2 = ma | (mb << 16);
         uint32_t mm = __funnelshift_l(m2, m2, swz << 4);  // swapped read order: swap the halves back
@@ -142,7 +133,7 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
     uint32_t r = __shfl_sync(0xffffffffu, tk, 0);
     if (r >= P.num_ranges) return;
 
-    // shared-window addresses (see kxparse4::lds128)
+    // shared-window addresses (see kxparse::lds128)
     uint32_t a_stage0 = smem_u32(smem_raw) + w * (uint32_t)sizeof(WarpSmem5);  // stage s: + s * STG_BYTES
     asm volatile("" : "+r"(a_stage0));  // opaque: keep it in a register instead of re-deriving it (S2R + LEA + IMAD) at every use
     const uint32_t a_bar0 = a_stage0 + (uint32_t)offsetof(WarpSmem5, bar);     // bar s:   + 8 * s
@@ -167,7 +158,7 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
         bool have_next = false;
         if (lane == 0) tk2 = atomicAdd(&P.tab.counters[KX_C_TICKET], 1u);
         // carry along the range: the governing line at the start of the next chunk as a status word
-        // (LS_* of pciids3.cu; 0 = not known) plus the chunk that holds the line (0xffffffff = the
+        // (LS_* of parse_common.cuh; 0 = not known) plus the chunk that holds the line (0xffffffff = the
         // shard's carry-in)
         uint32_t rc_x = 0, rc_g = 0;
         if (r == 0u) {
@@ -372,24 +363,45 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
 }
 
 // Resolve, step 1: the leading chunks of every range, whose governing line was not known to the
-// warp that parsed them.  One thread per range walks back over the range status words (all
-// published now).  The governing line is dead for all but the first copy of a vendor block; only
-// then the range's leading chunks are queued for step 2.
+// warp that parsed them.  One lane per range; the governing line is the inclusive carry of the
+// nearest earlier range that published one (all status words are final now).  The look-back is
+// warp-cooperative: 32 status words per step, first inside the warp's own 32 ranges, then
+// backwards 32 at a time -- one step for real data, at most num_ranges/32 steps for a text whose
+// top-level lines are megabytes apart.  The governing line is dead for all but the first copy of
+// a vendor block; only then the range's leading chunks are queued for step 2.
 __global__ void __launch_bounds__(256) resolve_ranges_kernel(const Params5 P) {
     const uint32_t rr = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rr >= P.num_ranges) return;
-    const uint32_t nlead = P.lead[rr];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t rr0 = rr - lane;  // first range of this warp
+    if (rr0 >= P.num_ranges) return;
+    const bool live = rr < P.num_ranges;
+    const uint32_t nlead = live ? P.lead[rr] : 0u;
+    // my own status word serves the lanes behind me
+    const unsigned long long own = live ? P.range_state[rr] : ST_NONE;
+    const uint32_t pm = __ballot_sync(0xffffffffu, (own & ST_MASK) == ST_PREFIX);
+    const uint32_t below = pm & ((1u << lane) - 1u);
+    const unsigned long long from_warp = __shfl_sync(0xffffffffu, own, below ? 31 - __clz((int)below) : 0);
+    // carry into the warp's first range (needed by the lanes in front of the warp's first prefix)
+    unsigned long long warp_in = 0;
+    const uint32_t first_p = pm ? (uint32_t)__ffs((int)pm) - 1u : 32u;
+    const bool want = __any_sync(0xffffffffu, nlead != 0u && lane <= first_p);
+    if (want) {
+        long long q0 = (long long)rr0 - 32;
+        for (;;) {
+            const long long q = q0 + lane;
+            const unsigned long long sv = q >= 0 ? P.range_state[q] : (q == -1 ? (ST_PREFIX | P.carry_in) : ST_NONE);
+            const uint32_t m = __ballot_sync(0xffffffffu, (sv & ST_MASK) == ST_PREFIX);
+            if (m) {
+                warp_in = __shfl_sync(0xffffffffu, sv, 31 - __clz((int)m));
+                break;
+            }
+            q0 -= 32;  // q == -1 (the shard's carry-in) always answers: the loop ends at the latest there
+        }
+    }
     if (nlead == 0u) return;
     // no top-level line between the start of the range and those chunks' head lines: the carry
     // into the range governs them
-    unsigned long long carry = 0;
-    for (long long q = (long long)rr - 1;; q--) {
-        const unsigned long long sv = q >= 0 ? P.range_state[q] : (ST_PREFIX | P.carry_in);
-        if ((sv & ST_MASK) == ST_PREFIX) {
-            carry = sv & ~ST_MASK;
-            break;
-        }
-    }
+    const unsigned long long carry = (below ? from_warp : warp_in) & ~ST_MASK;
     const bool alive = (carry & CV_HAS_TOP) && (carry & CV_VOK) &&
                        P.tab.vendor_first[(uint32_t)(carry >> 44) & 0xffffu] >= (carry & CV_ANCHOR_MASK);  // vendor_first is final here
     if (!alive) return;

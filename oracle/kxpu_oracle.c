@@ -510,3 +510,148 @@ double kxo_bench_parse_once(const uint8_t *text, size_t n, const uint32_t *keys,
     if (parse_s) *parse_s = t1 - t0;
     return t2 - t0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* "Best honest CPU" on ALL host threads: the text is cut into one shard per    */
+/* thread where a top-level line starts (the same rule as kxpu_plan_shards),    */
+/* every thread runs the single pass of kxo_table_build on its shard (device    */
+/* lines under a vendor id it has already seen are skipped unparsed, exactly    */
+/* the first-occurrence shortcut the GPU kernel uses), then the shards' first   */
+/* anchors are min-merged and the rows whose anchor is the global first one are */
+/* concatenated in shard (= file) order.  Equals kxo_table_build on the whole   */
+/* text (tests/test_oracle.py).  Keys are probed by binary search, in parallel. */
+/* ------------------------------------------------------------------------- */
+static size_t kxo_next_top(const uint8_t *text, size_t n, size_t pos) {
+    if (pos == 0) return 0;
+    if (pos >= n) return n;
+    size_t p = pos;
+    if (text[p - 1] != '\n') {
+        const uint8_t *nl = (const uint8_t *)memchr(text + p, '\n', n - p);
+        if (!nl) return n;
+        p = (size_t)(nl - text) + 1;
+    }
+    while (p < n) {
+        if (text[p] != '\t' && text[p] != '#') return p;
+        const uint8_t *nl = (const uint8_t *)memchr(text + p, '\n', n - p);
+        if (!nl) return n;
+        p = (size_t)(nl - text) + 1;
+    }
+    return n;
+}
+
+typedef struct {
+    const uint8_t *text; size_t n, lo, hi;  /* shard [lo,hi) of text[0..n) */
+    kxo_row *rows; size_t nrows, cap;
+    uint64_t *vfirst;                       /* [65536] first anchor of the shard per vendor, ~0 = none */
+    uint64_t trunc;                         /* offset where the scan stops (ErrTooLong), ~0 = never */
+} kxo_shard_job;
+
+static void *shard_worker(void *arg) {
+    kxo_shard_job *j = (kxo_shard_job *)arg;
+    uint8_t *dev_seen = (uint8_t *)calloc(65536 / 8, 1);
+    size_t pos = j->lo, ls, le;
+    int cur_valid = 0, rc;
+    uint32_t cur_v = 0;
+    uint64_t cur_anchor = 0;
+    j->nrows = 0; j->trunc = ~0ull;
+    memset(j->vfirst, 0xff, 65536 * sizeof(uint64_t));
+    while ((rc = kxo_next_line(j->text, j->hi, &pos, &ls, &le)) == 1) {
+        size_t len = le - ls;
+        const uint8_t *l = j->text + ls;
+        if (len >= 1 && l[0] == '#') continue;
+        if (len >= 1 && l[0] == '\t') {
+            uint32_t d;
+            if (cur_valid && parse_hex4(l + 1, len - 1, &d) && !(dev_seen[d >> 3] & (1u << (d & 7)))) {
+                dev_seen[d >> 3] |= (uint8_t)(1u << (d & 7));
+                if (j->nrows == j->cap) { j->cap = j->cap ? j->cap * 2 : 4096; j->rows = (kxo_row *)realloc(j->rows, j->cap * sizeof(kxo_row)); }
+                j->rows[j->nrows].key = (cur_v << 16) | d; j->rows[j->nrows].line_off = ls; j->rows[j->nrows].anchor_off = cur_anchor;
+                j->nrows++;
+            }
+            continue;
+        }
+        cur_valid = 0;
+        uint32_t v;
+        if (parse_hex4(l, len, &v) && j->vfirst[v] == ~0ull) {
+            j->vfirst[v] = ls;
+            cur_valid = 1; cur_v = v; cur_anchor = ls;
+            memset(dev_seen, 0, 65536 / 8);
+        }
+    }
+    if (rc == -1) j->trunc = pos;
+    free(dev_seen);
+    return NULL;
+}
+
+/* rows_out (may be NULL) receives up to cap rows in file order; returns the row count */
+size_t kxo_table_build_mt(const uint8_t *text, size_t n, int threads, kxo_row *rows_out, size_t cap) {
+    if (threads < 1) threads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    kxo_shard_job *jobs = (kxo_shard_job *)calloc((size_t)threads, sizeof(kxo_shard_job));
+    size_t cut = 0;
+    for (int t = 0; t < threads; t++) {
+        size_t next = t + 1 == threads ? n : kxo_next_top(text, n, (size_t)((unsigned __int128)n * (unsigned)(t + 1) / (unsigned)threads));
+        if (next < cut) next = cut;
+        jobs[t].text = text; jobs[t].n = n; jobs[t].lo = cut; jobs[t].hi = next;
+        jobs[t].vfirst = (uint64_t *)malloc(65536 * sizeof(uint64_t));
+        cut = next;
+        pthread_create(&th[t], NULL, shard_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    uint64_t *gfirst = (uint64_t *)malloc(65536 * sizeof(uint64_t));
+    memset(gfirst, 0xff, 65536 * sizeof(uint64_t));
+    uint64_t trunc = ~0ull;
+    for (int t = 0; t < threads; t++) {
+        for (uint32_t v = 0; v < 65536; v++) if (jobs[t].vfirst[v] < gfirst[v]) gfirst[v] = jobs[t].vfirst[v];
+        if (jobs[t].trunc < trunc) trunc = jobs[t].trunc;
+    }
+    size_t nr = 0;
+    for (int t = 0; t < threads; t++) {
+        for (size_t i = 0; i < jobs[t].nrows; i++) {
+            const kxo_row *r = &jobs[t].rows[i];
+            /* a top-level line is a valid anchor only in front of the cut-off, a row only in front of it too */
+            if (r->anchor_off == gfirst[r->key >> 16] && r->line_off < trunc) {
+                if (rows_out && nr < cap) rows_out[nr] = *r;
+                nr++;
+            }
+        }
+        free(jobs[t].rows); free(jobs[t].vfirst);
+    }
+    free(gfirst); free(th); free(jobs);
+    return nr;
+}
+
+typedef struct { const kxo_row *rows; size_t nr; const uint32_t *keys; size_t lo, hi; int64_t *line_off; } kxo_probe_job;
+static void *probe_worker(void *arg) {
+    kxo_probe_job *j = (kxo_probe_job *)arg;
+    for (size_t i = j->lo; i < j->hi; i++) {
+        kxo_row k; k.key = j->keys[i];
+        const kxo_row *r = (const kxo_row *)bsearch(&k, j->rows, j->nr, sizeof(kxo_row), row_cmp);
+        if (j->line_off) j->line_off[i] = r ? (int64_t)r->line_off : -1;
+    }
+    return NULL;
+}
+
+/* parse on `threads` threads + parallel probes; returns total seconds, *parse_s = parse + merge */
+double kxo_bench_parse_mt(const uint8_t *text, size_t n, int threads, const uint32_t *keys, size_t nkeys,
+                          int64_t *line_off, double *parse_s) {
+    if (threads < 1) threads = 1;
+    double t0 = now_s();
+    size_t cap = 1u << 16;
+    kxo_row *rows = (kxo_row *)malloc(cap * sizeof(kxo_row));
+    size_t nr = kxo_table_build_mt(text, n, threads, rows, cap);
+    if (nr > cap) { cap = nr; rows = (kxo_row *)realloc(rows, cap * sizeof(kxo_row)); nr = kxo_table_build_mt(text, n, threads, rows, cap); }
+    double t1 = now_s();
+    qsort(rows, nr, sizeof(kxo_row), row_cmp);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    kxo_probe_job *pj = (kxo_probe_job *)calloc((size_t)threads, sizeof(kxo_probe_job));
+    for (int t = 0; t < threads; t++) {
+        pj[t].rows = rows; pj[t].nr = nr; pj[t].keys = keys; pj[t].line_off = line_off;
+        pj[t].lo = nkeys * (size_t)t / (size_t)threads; pj[t].hi = nkeys * (size_t)(t + 1) / (size_t)threads;
+        pthread_create(&th[t], NULL, probe_worker, &pj[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    double t2 = now_s();
+    free(th); free(pj); free(rows);
+    if (parse_s) *parse_s = t1 - t0;
+    return t2 - t0;
+}

@@ -78,6 +78,11 @@ def lib():
         L.kxo_bench_parse_once.restype = C.c_double
         L.kxo_bench_parse_once.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
                                            C.POINTER(C.c_double)]
+        L.kxo_table_build_mt.restype = C.c_size_t
+        L.kxo_table_build_mt.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
+        L.kxo_bench_parse_mt.restype = C.c_double
+        L.kxo_bench_parse_mt.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                         C.POINTER(C.c_double)]
         _LIB = L
     return _LIB
 
@@ -210,4 +215,26 @@ def bench_parse_once(text, keys):
     offs = np.empty(len(keys), np.int64)
     ps = C.c_double(0)
     dt = lib().kxo_bench_parse_once(p, n, keys.ctypes.data, len(keys), offs.ctypes.data, C.byref(ps))
+    return dt, ps.value, offs
+
+
+def table_build_mt(text, threads):
+    """kxo_table_build on `threads` host threads (shards cut at vendor lines, first anchors merged)."""
+    p, n, keep = _buf(text)
+    cap = 1 << 16
+    rows = np.zeros(cap, dtype=ROW_DTYPE)
+    nr = lib().kxo_table_build_mt(p, n, threads, rows.ctypes.data, cap)
+    if nr > cap:
+        rows = np.zeros(nr, dtype=ROW_DTYPE)
+        nr = lib().kxo_table_build_mt(p, n, threads, rows.ctypes.data, nr)
+    return rows[:nr]
+
+
+def bench_parse_mt(text, keys, threads):
+    """(total seconds, parse seconds, line_off[]) of the all-threads single-pass CPU path."""
+    p, n, keep = _buf(text)
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    offs = np.empty(len(keys), np.int64)
+    ps = C.c_double(0)
+    dt = lib().kxo_bench_parse_mt(p, n, threads, keys.ctypes.data, len(keys), offs.ctypes.data, C.byref(ps))
     return dt, ps.value, offs

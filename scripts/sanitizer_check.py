@@ -18,3 +18,23 @@ devs = W.cfg5_devices(3000)
 print("classify", res["n_accepted"], "json", len(kx.cdi_emit(1, devs)), "yaml", len(kx.cdi_emit(0, devs)))
 print("alloc", len(kx.alloc_names(devs["index"])[0]), "lw", len(kx.lw_encode(res["group_ids"][:100])))
 tab.free()
+# sharded load + join, three contexts of one process on this GPU
+m = K.KxpuMulti([0, 0, 0])
+big = text * 2
+q = W.cfg2_queries(keys)[:768]
+shards, bufs = [], []
+for r, (a, b) in enumerate(K.plan_shards(big, 3)):
+    k2 = m.ctxs[r]
+    d = k2.dev_alloc(max(b - a, 16)); k2.upload(d, np.frombuffer(big[a:b], np.uint8))
+    dq, dr = k2.dev_alloc(256 * 4), k2.dev_alloc(768 * 4)
+    k2.upload(dq, q[256 * r:256 * r + 256])
+    shards.append(dict(d_text=d, n=b - a, global_base=a, d_keys=dq, nq=256, key_offset=256 * r, d_rows_all=dr))
+    bufs.append((k2, d, dq, dr))
+for rep in range(3):
+    tabs = m.pciids_join(shards, 768)
+    print("sharded rows", [t.rows for t in tabs], "hits", int((m.ctxs[0].download(shards[0]["d_rows_all"], 768 * 4, np.int32) >= 0).sum()))
+    for t in tabs:
+        t.free()
+for k2, d, dq, dr in bufs:
+    k2.dev_free(d); k2.dev_free(dq); k2.dev_free(dr)
+m.close()

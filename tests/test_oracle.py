@@ -229,3 +229,18 @@ def test_classify_vs_python(oracle, workloads, oracle_rows):
 def test_lw_encode(oracle):
     b = oracle.lw_encode(np.array([214, 7], np.uint32), np.array([1, 0], np.uint8))
     assert b == (b"\x0a\x0e\x0a\x03214\x12\x07Healthy" + b"\x0a\x0e\x0a\x017\x12\x09Unhealthy")
+
+
+def test_all_threads_single_pass_equals_sequential(oracle, pci_text):
+    """kxo_table_build_mt (the all-cores CPU comparator of bench.py: shards cut at vendor lines, first
+    anchors min-merged) == kxo_table_build on the whole text, incl. duplicates across shards and a
+    >= 64 KiB line in a middle shard."""
+    texts = [pci_text, pci_text * 3, pci_text[700000:pci_text.find(b"\n", 1400000) + 1] + pci_text, b"", b"\tx\n",
+             b"1111  one\n\t0001  a\n" * 300 + b"3333  " + b"x" * 70000 + b"\n\t0003  hidden\n" + b"4444  f\n\t0004  h\n" * 300]
+    for t in texts:
+        want = oracle.table_build(t)
+        for th in (1, 2, 3, 8, 33):
+            got = oracle.table_build_mt(t, th)
+            assert np.array_equal(want, got), (len(t), th)
+    dt, ps, offs = oracle.bench_parse_mt(pci_text * 2, oracle.table_build(pci_text)["key"][:500], 4)
+    assert np.array_equal(offs, oracle.table_build(pci_text)["line_off"][:500].astype(np.int64)) and 0 < ps <= dt
