@@ -355,10 +355,12 @@ def main():
         clocks = sampler.stop() if sampler is not None else None
         km = {k: [] for k in ("parse", "parse_resolve", "finalize", "merge", "lookup")}
         for _ in range(min(steps, 10)):
-            t = w["step"]()
+            t = w["load"]()  # the load half of the step (N > 1: collective), then the join of this rank's keys
             tm = kx.timings()
             km["parse"].append(tm[B.T_PARSE]); km["parse_resolve"].append(tm[B.T_RESOLVE]); km["finalize"].append(tm[B.T_FINALIZE])
-            km["merge"].append(tm[B.T_MERGE]); km["lookup"].append(tm[B.T_LOOKUP])
+            km["merge"].append(tm[B.T_MERGE])
+            kx.lookup_device(t, w["d_keys"], w["nq"], w["d_rows"])
+            km["lookup"].append(kx.timings()[B.T_LOOKUP])
             t.free()
         ms_step = max_over_ranks(ms_total) / steps
         return dict(ms_per_step=ms_step, value=w["job_bytes"] / (ms_step * 1e-3) / 1e9, wall_ms_per_step=wall_ms / steps,
@@ -485,7 +487,7 @@ def main():
                             "the table (2.6 MB) always is: a throughput figure, not an HBM roofline",
             "kernel_ms": km, "limiting_stage": limiting,
             "kernel_ms_note": "device time per stage on rank 0 from separate passes with per-stage CUDA events; "
-                              "merge = phase A push .. insert of the winners (includes waiting for the slowest rank)",
+                              "merge = wait for phase A .. insert of the winners (contains the finalize of the winners and the waits for the slowest rank)",
             "wall_ms_per_step": head["wall_ms_per_step"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic() if world == 1 else None, "peak_source": peak_src,

@@ -314,15 +314,23 @@ class Kxpu:
     def cdi_emit(self, fmt, devs):
         devs = np.ascontiguousarray(devs)
         assert devs.dtype == CDIDEV_DTYPE
+        # one call with a buffer no document can outgrow (<= 384 B per device); the two-call sizing
+        # protocol (out = NULL -> *len) remains available and is exercised by the tests
+        cap = 400 * len(devs) + 1024
+        out = np.empty(cap, np.uint8)
+        got = C.c_size_t(0)
+        self._chk(self.L.kxpu_cdi_emit(self.ctx, fmt, _ptr(devs) if len(devs) else None, len(devs), _ptr(out), cap,
+                                       C.byref(got)))
+        return out[:got.value].tobytes()
+
+    def cdi_emit_len(self, fmt, devs):
+        """Sizing call of the two-call protocol: out = NULL, returns the required length."""
+        devs = np.ascontiguousarray(devs)
         need = C.c_size_t(0)
         rc = self.L.kxpu_cdi_emit(self.ctx, fmt, _ptr(devs) if len(devs) else None, len(devs), None, 0, C.byref(need))
         if rc not in (KXPU_OK, E_NOSPACE):
             self._chk(rc)
-        out = np.empty(max(need.value, 1), np.uint8)
-        got = C.c_size_t(0)
-        self._chk(self.L.kxpu_cdi_emit(self.ctx, fmt, _ptr(devs) if len(devs) else None, len(devs), _ptr(out),
-                                       need.value, C.byref(got)))
-        return out[:got.value].tobytes()
+        return need.value
 
     def alloc_names(self, idx):
         idx = np.ascontiguousarray(idx, dtype=np.uint64)

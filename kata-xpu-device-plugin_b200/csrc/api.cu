@@ -338,12 +338,12 @@ uint32_t kx_initial_blob_cap(kxpu_ctx *ctx, size_t n) {
     return ctx->blob_hint > by_text ? ctx->blob_hint : by_text;
 }
 
-bool kx_grow_cap(uint32_t *cap, size_t n_text) {
+bool kx_grow_cap(uint32_t *cap, bool table_full) {
     if (*cap >= (1u << 28)) return false;
-    // a device line is at least 6 bytes; real pci.ids has one per ~77 bytes of text
-    uint32_t want = *cap << 2;
-    while (want < (1u << 28) && (size_t)want < n_text / 32) want <<= 1;
-    *cap = want;
+    // x4 when the load limit was crossed (the key count is known to be below cap), x16 when the
+    // table ran full (the count is unknown)
+    const uint32_t sh = table_full ? 4u : 2u;
+    *cap = (*cap >> (28u - sh)) ? (1u << 28) : (*cap << sh);
     return true;
 }
 
@@ -356,11 +356,21 @@ void kx_note_table_size(kxpu_ctx *ctx, uint32_t nkeys, uint32_t blob_used, uint3
 
 // ------------------------------------------------------------------ launches
 int32_t kx_launch_parse(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base,
-                        unsigned long long carry_in) {
+                        unsigned long long carry_in, const KxXaHook *xa) {
     using namespace kxparse;
     const uint32_t num_chunks = (uint32_t)((n + CW - 1) / CW);
-    if (num_chunks == 0) return KXPU_OK;
     kxparse5::Params5 P;
+    memset(&P, 0, sizeof P);
+    if (xa) { P.xa_on = 1; P.xa_done = xa->done; P.xa = xa->p; }
+    if (num_chunks == 0) {
+        if (xa) {  // an empty shard still takes part in the exchange
+            P.tab = t->dev;
+            kxparse5::resolve_chunks_kernel<<<1, kxparse5::RES_WARPS * 32, 0, ctx->stream>>>(P);
+            KX_LAUNCHED(ctx);
+            KX_CUDA(ctx, cudaGetLastError());
+        }
+        return KXPU_OK;
+    }
     P.text = d_text; P.n = n; P.base = base; P.num_chunks = num_chunks;
     P.tma_limit = n >= (size_t)STG_BYTES ? (uint32_t)((n - STG_BYTES) / CW) + 1u : 0u;
     static int per_sm = 0;
@@ -408,8 +418,10 @@ int32_t kx_launch_trunc(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, siz
 }
 
 int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base,
-                           const unsigned long long *vendor_first, const unsigned long long *trunc) {
+                           const unsigned long long *vendor_first, const unsigned long long *trunc, const kxx::WaitSpec *wait) {
     kxparse::FinalizeParams F;
+    memset(&F, 0, sizeof F);
+    if (wait) F.wait = *wait;
     F.text = d_text; F.n = n; F.base = base; F.tab = t->dev;
     F.vendor_first = vendor_first ? vendor_first : t->dev.vendor_first;
     F.trunc = trunc ? trunc : t->dev.trunc;
@@ -418,8 +430,9 @@ int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, 
     F.blob = t->blob; F.blob_cap = t->blob_cap;
     KxTimer tm(ctx, KXPU_T_FINALIZE);
     kxparse::finalize_select_kernel<<<(t->cap + 1 + 255) / 256, 256, 0, ctx->stream>>>(F);
-    // one warp per selected slot; CTAs beyond the (device-side) count exit at once
-    kxparse::finalize_kernel<<<(t->cap + 1 + kxparse::FIN_WARPS - 1) / kxparse::FIN_WARPS, kxparse::FIN_WARPS * 32, 0, ctx->stream>>>(F);
+    // one warp per selected slot, persistent grid (the count lives on the device)
+    const unsigned fin_grid = std::min<unsigned>((t->cap + 1 + kxparse::FIN_WARPS - 1) / kxparse::FIN_WARPS, 8u * ctx->sm_count);
+    kxparse::finalize_kernel<<<fin_grid, kxparse::FIN_WARPS * 32, 0, ctx->stream>>>(F);
     ctx->launches += 2;
     KX_CUDA(ctx, cudaGetLastError());
     return KXPU_OK;
@@ -460,11 +473,11 @@ static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t 
         kxpu_table *t = nullptr;
         int32_t rc = kx_table_acquire(ctx, cap, blob_cap, num_chunks, &t);
         if (rc != KXPU_OK) return rc;
-        rc = kx_launch_parse(ctx, t, d_text, n, 0, 0);
+        rc = kx_launch_parse(ctx, t, d_text, n, 0, 0, nullptr);
         // a text with a >= 2 KiB stretch without a newline was seen on an earlier attempt: the exact
         // bufio.ErrTooLong cut-off is computed before the finalize
         if (rc == KXPU_OK && have_trunc) rc = kx_launch_trunc(ctx, t, d_text, n, 0);
-        if (rc == KXPU_OK) rc = kx_launch_finalize(ctx, t, d_text, n, 0, nullptr, nullptr);
+        if (rc == KXPU_OK) rc = kx_launch_finalize(ctx, t, d_text, n, 0, nullptr, nullptr, nullptr);
         // the join does not need anything from the host: enqueue it before the round trip below
         // (it is simply run again if the table has to be rebuilt)
         if (rc == KXPU_OK && join) rc = kx_launch_lookup(ctx, t, join->d_keys, join->n, join->d_rows);
@@ -479,7 +492,7 @@ static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t 
         const uint32_t *h = ctx->h_ctl;
         if (h[KX_C_OVERFLOW] || h[KX_C_NKEYS] > t->dev.max_keys) {
             kx_table_release(ctx, t);
-            if (!kx_grow_cap(&cap, n)) return KXPU_E_CAPACITY;
+            if (!kx_grow_cap(&cap, h[KX_C_OVERFLOW] != 0)) return KXPU_E_CAPACITY;
             continue;
         }
         if (h[KX_C_NEED_TRUNC] == 2u) {  // finalize stood back: run again with the cut-off (never for real pci.ids)

@@ -35,6 +35,7 @@
 #include <algorithm>
 #include <new>
 
+#include "exchange.cuh"
 #include "internal.cuh"
 #include "parse_common.cuh"
 
@@ -84,15 +85,6 @@ static bool nccl_load() {
 }
 
 // ------------------------------------------------------------------ exchange region
-constexpr uint32_t XS_GROW = 1u;           // a rank's table overflowed / is too full
-constexpr uint32_t XS_NEED_TRUNC = 2u;     // a rank saw a possible >= 64 KiB line: run again with exact cut-offs
-constexpr uint32_t XS_SLAB_OVERFLOW = 4u;  // a rank's winners outgrow the slab
-constexpr uint32_t XS_GROW_BLOB = 8u;      // a rank's name blob is too small
-constexpr int XS_BITS = 4;
-
-constexpr int A_TRUNC = 65536;       // phase-A block: u64 [65536] vendor_first | trunc | XS_BITS status words | pad
-constexpr int A_STATUS0 = 65537;     // status bit k is set iff word A_STATUS0 + k == 0 (so that min all-reduces it)
-constexpr int A_WORDS = 65536 + 8;
 constexpr size_t FLAGS_BYTES = 1024;  // u32 flag[3 phases][2 buffers][KX_MAX_RANKS]
 
 struct XCaps { uint32_t rows, blob, join; };  // per-rank slab rows / name bytes, keys of one sharded join
@@ -127,11 +119,6 @@ __host__ __device__ static inline size_t flag_off(int phase, int b, int rank) { 
 
 static const XCaps kPeerCaps{65536u, 2u << 20, 1u << 21};
 
-struct Targets {  // where a push goes: every rank's region (peer memory) or this rank's staging region (NCCL)
-    uint8_t *region[KX_MAX_RANKS];
-    int n;
-};
-
 }  // namespace kxx
 
 struct KxExchange {
@@ -140,6 +127,7 @@ struct KxExchange {
     bool ipc = false;     // peers mapped through CUDA IPC (else direct pointers of this process)
     bool broken = false;  // a time-out / CUDA error desynchronised the ranks: re-init required
     bool use_nccl = false;  // transport of the current/next attempt
+    bool fuse_waits = false;  // every rank has its own GPU: consumer kernels wait for the flags in their prologue
     uint8_t *local = nullptr;
     uint8_t *peer[KX_MAX_RANKS] = {};
     kxx::XLayout L{};
@@ -158,70 +146,9 @@ struct KxExchange {
 namespace kxx {
 
 // ------------------------------------------------------------------ kernels
-struct XaParams {
-    Targets tg;
-    uint8_t *mine;            // my region (the next buffer's phase-A block is cleared here)
-    size_t o_a, o_a_next;     // phase-A block of this / the next epoch inside a region
-    int clear_next;
-    size_t o_flag;            // my phase-A flag inside a region (peer transport)
-    int raise_flags;
-    uint32_t epoch;
-    const unsigned long long *vendor_first, *trunc;
-    const uint32_t *counters;
-    uint32_t max_keys;
-    int have_trunc;
-    uint32_t *done;
-};
-
-// Phase A: vendor_first / cut-off / status of this shard, min-reduced into every rank's region.
-__global__ void __launch_bounds__(256) xa_push_kernel(const XaParams P) {
-    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;  // 65536 threads
-    if (P.clear_next) {
-        unsigned long long *nx = reinterpret_cast<unsigned long long *>(P.mine + P.o_a_next);
-        nx[v] = KX_NO_OFF;
-        if (v < (uint32_t)(A_WORDS - 65536)) nx[65536 + v] = KX_NO_OFF;
-    }
-    const unsigned long long f = P.vendor_first[v];
-    if (f != KX_NO_OFF)
-        for (int q = 0; q < P.tg.n; q++) atomicMin(reinterpret_cast<unsigned long long *>(P.tg.region[q] + P.o_a) + v, f);
-    if (v == 0) {
-        const unsigned long long t = *P.trunc;
-        uint32_t st = 0;
-        if (P.counters[KX_C_OVERFLOW] || P.counters[KX_C_NKEYS] > P.max_keys) st |= XS_GROW;
-        if (P.counters[KX_C_LONGLINE_HINT] && !P.have_trunc) st |= XS_NEED_TRUNC;
-        for (int q = 0; q < P.tg.n; q++) {
-            unsigned long long *a = reinterpret_cast<unsigned long long *>(P.tg.region[q] + P.o_a);
-            if (t != KX_NO_OFF) atomicMin(a + A_TRUNC, t);
-            for (int k = 0; k < XS_BITS; k++)
-                if ((st >> k) & 1u) atomicMin(a + A_STATUS0 + k, 0ull);
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t prev = atomicAdd(P.done, 1u);
-        if (prev == gridDim.x - 1u) {
-            *P.done = 0u;
-            __threadfence_system();
-            if (P.raise_flags)
-                for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[q] + P.o_flag) = P.epoch;
-            __threadfence_system();
-        }
-    }
-}
-
-// one warp: lane q waits for rank q's flag of this epoch
-__global__ void wait_flags_kernel(const uint32_t *flags, int nranks, uint32_t epoch, uint32_t *timeout_flag) {
-    const int q = threadIdx.x;
-    if (q < nranks) {
-        const long long t0 = clock64();
-        while (*reinterpret_cast<const volatile uint32_t *>(&flags[q]) != epoch) {
-            __nanosleep(100);
-            if (clock64() - t0 > 8000000000ll) { *timeout_flag = 1u; break; }  // ~4 s: a peer died or the ranks lost step
-        }
-    }
-    __threadfence_system();
-}
+// one warp: lane q waits for rank q's flag of this epoch (used when the wait cannot ride on the
+// consumer kernel: several contexts share one GPU and many spinning CTAs could starve the peers)
+__global__ void wait_flags_kernel(const WaitSpec W) { wait_flags_lane(W, (int)threadIdx.x); }
 
 struct XbParams {
     Targets tg;
@@ -260,9 +187,11 @@ __global__ void __launch_bounds__(256) xb_push_kernel(const XbParams P) {
             for (int q = 0; q < P.tg.n; q++) reinterpret_cast<uint4 *>(P.tg.region[q] + P.o_slab + slab_blob_off(P.rows_cap))[i] = x;
         }
     }
-    __threadfence_system();
+    // one system fence per CTA: the barrier makes the CTA's pushes visible to thread 0, whose
+    // (cumulative) fence orders them in front of the counter and, in the last CTA, of the flags
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const uint32_t prev = atomicAdd(P.done, 1u);
         if (prev == gridDim.x - 1u) {
             *P.done = 0u;
@@ -282,6 +211,11 @@ __global__ void __launch_bounds__(256) xb_push_kernel(const XbParams P) {
     }
 }
 
+// keys a table may hold after the merge: the bound (winners + the most losers any rank keeps) is the
+// same on every rank and usually counts the winners' keys twice, so it may go well beyond the 50 %
+// load the parse is held to
+__host__ __device__ static inline uint32_t merged_key_limit(uint32_t cap) { return cap - cap / 8; }
+
 struct MergeParams {
     const uint8_t *slabs;  // slab of rank 0; rank r at + r * stride
     size_t stride;
@@ -294,6 +228,7 @@ struct MergeParams {
     uint8_t *blob;
     uint32_t rows_cap, blob_cap;
     const uint32_t *timeout_flag;
+    WaitSpec wait;
 };
 
 // The winners of all ranks go into the table this rank parsed into: row arrays and names at their
@@ -302,6 +237,7 @@ struct MergeParams {
 // (KX_C_X*) from the same headers and takes the same retry decision from it.
 __global__ void __launch_bounds__(256) merge_kernel(const MergeParams P) {
     __shared__ uint32_t rpre[KX_MAX_RANKS + 1], bpre[KX_MAX_RANKS + 1], s_status, s_maxkeys;
+    wait_flags_cta(P.wait);
     if (threadIdx.x == 0) {
         uint32_t st = 0, mk = 0, racc = 0, bacc = 0;
         for (int k = 0; k < XS_BITS; k++)
@@ -312,7 +248,8 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeParams P) {
             racc += h->n_rows;
             bacc += (h->blob_bytes + 15u) & ~15u;
             st |= h->status;
-            mk = h->nkeys > mk ? h->nkeys : mk;
+            const uint32_t losers = h->nkeys > h->n_rows ? h->nkeys - h->n_rows : 0u;  // local keys that are not winners
+            mk = losers > mk ? losers : mk;
         }
         rpre[P.R] = racc; bpre[P.R] = bacc;
         if (P.timeout_flag && *P.timeout_flag) st |= 0x80000000u;
@@ -327,8 +264,9 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeParams P) {
     __syncthreads();
     const uint32_t total_rows = rpre[P.R], total_b16 = bpre[P.R] / 16u;
     // uniform on every rank: table capacities are kept equal across ranks (KxExchange::x_cap)
-    if (s_status != 0u || total_rows > P.rows_cap || bpre[P.R] > P.blob_cap || total_rows + s_maxkeys > P.tab.max_keys) return;
+    if (s_status != 0u || total_rows > P.rows_cap || bpre[P.R] > P.blob_cap || total_rows + s_maxkeys > merged_key_limit(P.tab.cap)) return;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    uint32_t nfresh = 0;
     for (size_t g = tid; g < total_rows; g += nth) {
         int r = 0;
         while (r + 1 < P.R && g >= rpre[r + 1]) r++;
@@ -336,9 +274,10 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeParams P) {
         const SlabRow row = reinterpret_cast<const SlabRow *>(slab + slab_rows_off())[g - rpre[r]];
         P.row_key[g] = row.key; P.row_line[g] = row.line; P.row_anchor[g] = row.anchor;
         P.row_name_off[g] = bpre[r] + row.name_off; P.row_name_len[g] = row.name_len;
-        const uint32_t slot = kxparse::table_claim(P.tab, row.key);
+        const uint32_t slot = kxparse::table_claim(P.tab, row.key, nfresh);
         if (slot != 0xffffffffu) P.tab.slots[slot].row = (int32_t)g;
     }
+    if (nfresh) atomicAdd(&P.tab.counters[KX_C_NKEYS], nfresh);
     for (size_t j = tid; j < total_b16; j += nth) {
         int r = 0;
         while (r + 1 < P.R && j * 16u >= bpre[r + 1]) r++;
@@ -371,9 +310,11 @@ __global__ void __launch_bounds__(256) join_gather_kernel(const JoinParams P) {
         const int32_t row = kxparse::table_probe(P.slots, P.cap, P.shift, P.keys[i]);
         for (int q = 0; q < P.tg.n; q++) reinterpret_cast<int32_t *>(P.tg.region[q] + P.o_res)[P.key_offset + i] = row;
     }
-    __threadfence_system();
+    // one system fence per CTA: the barrier makes the CTA's pushes visible to thread 0, whose
+    // (cumulative) fence orders them in front of the counter and, in the last CTA, of the flags
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const uint32_t prev = atomicAdd(P.done, 1u);
         if (prev == gridDim.x - 1u) {
             *P.done = 0u;
@@ -383,6 +324,15 @@ __global__ void __launch_bounds__(256) join_gather_kernel(const JoinParams P) {
             __threadfence_system();
         }
     }
+}
+
+// everybody's hits have landed in my result buffer: hand them to the caller's buffer
+__global__ void __launch_bounds__(256) gather_copy_kernel(const WaitSpec W, const uint4 *src, uint4 *dst, size_t n16, const int32_t *src_tail,
+                                                          int32_t *dst_tail, uint32_t n_tail) {
+    wait_flags_cta(W);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x < n_tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
 }
 
 __global__ void fill_ff_kernel(uint4 *p, size_t n16) {
@@ -472,6 +422,7 @@ static void ipc_setup(kxpu_ctx *ctx, KxExchange *x) {
     }
     x->ipc = true;
     x->p2p = true;
+    x->fuse_waits = true;  // one process per rank, one GPU per process
     if (getenv("KXPU_TRACE_MERGE")) fprintf(stderr, "[kxpu] rank %d: peer-memory exchange over %d ranks, %zu B per rank\n", x->rank, R, x->L.total);
 }
 
@@ -518,6 +469,36 @@ struct ShardOp {
     int32_t rc = KXPU_OK;  // first failure of an enqueue phase (the remaining phases are skipped)
 };
 
+// KXPU_TRACE_MERGE=1: device time between the enqueue points of one sharded load, averaged over 16 loads
+struct PhaseTrace {
+    static constexpr int N = 10;
+    cudaEvent_t ev[N] = {};
+    bool on = false, made = false;
+    double acc[N] = {};
+    int calls = 0;
+    const char *name[N] = {"trunc", "parse+resolve+xa", "waitA", "select+finalize", "xb_push", "waitB", "merge", "join", "waitC+copy", ""};
+    void init() {
+        on = getenv("KXPU_TRACE_MERGE") != nullptr;
+        if (on && !made) { for (auto &e : ev) cudaEventCreate(&e); made = true; }
+    }
+    void mark(int i, cudaStream_t s) { if (on) cudaEventRecord(ev[i], s); }
+    void report(int rank, int nranks) {
+        if (!on) return;
+        for (int i = 0; i + 1 < N; i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) acc[i] += ms;
+        }
+        cudaGetLastError();
+        if (++calls % 16 == 0) {
+            fprintf(stderr, "[kxpu shard trace] rank %d/%d:", rank, nranks);
+            for (int i = 0; i + 1 < N; i++) fprintf(stderr, " %s %.1f us |", name[i], acc[i] / 16 * 1e3);
+            fprintf(stderr, "\n");
+            for (auto &a : acc) a = 0;
+        }
+    }
+};
+static thread_local PhaseTrace g_trace;
+
 static Targets targets(const ShardOp &op) {
     Targets tg;
     memset(&tg, 0, sizeof tg);
@@ -562,21 +543,27 @@ static void shard_phase1(ShardOp &op) {
     op.rc = kx_table_acquire(ctx, x->x_cap, x->x_blob_cap, num_chunks, &op.t);
     if (op.rc != KXPU_OK) return;
     kxpu_table *t = op.t;
-    op.rc = kx_launch_parse(ctx, t, op.a.d_text, op.a.n, op.a.base, 0);
-    if (op.rc == KXPU_OK && op.have_trunc) op.rc = kx_launch_trunc(ctx, t, op.a.d_text, op.a.n, op.a.base);
+    g_trace.init();
+    g_trace.mark(0, ctx->stream);
+    // exact bufio.ErrTooLong cut-off of the shard (second attempt only; independent of the parse)
+    if (op.have_trunc) op.rc = kx_launch_trunc(ctx, t, op.a.d_text, op.a.n, op.a.base);
     if (op.rc != KXPU_OK) return;
-    if (ctx->stage_timing) cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE], ctx->stream);
+    g_trace.mark(1, ctx->stream);
+    // parse + resolve; the last CTA of the resolve kernel pushes the shard's minima (phase A)
     const XLayout &L = layout(op);
-    XaParams P;
-    memset(&P, 0, sizeof P);
+    KxXaHook hook;
+    memset(&hook, 0, sizeof hook);
+    XaParams &P = hook.p;
     P.tg = targets(op);
     P.mine = my_region(op);
     P.o_a = L.o_a[op.b]; P.o_a_next = L.o_a[op.b ^ 1]; P.clear_next = op.nccl ? 0 : 1;
     P.o_flag = flag_off(0, op.b, x->rank); P.raise_flags = op.nccl ? 0 : 1; P.epoch = op.epoch;
     P.vendor_first = t->dev.vendor_first; P.trunc = t->dev.trunc; P.counters = t->dev.counters;
-    P.max_keys = t->dev.max_keys; P.have_trunc = op.have_trunc ? 1 : 0; P.done = x->scratch + 0;
-    xa_push_kernel<<<65536 / 256, 256, 0, ctx->stream>>>(P);
-    KX_LAUNCHED(ctx);
+    P.max_keys = t->dev.max_keys; P.have_trunc = op.have_trunc ? 1 : 0;
+    hook.done = x->scratch + 0;
+    op.rc = kx_launch_parse(ctx, t, op.a.d_text, op.a.n, op.a.base, 0, &hook);
+    if (ctx->stage_timing) cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE], ctx->stream);  // exchange: wait A .. winners inserted
+    g_trace.mark(2, ctx->stream);
 }
 
 // phase 2: global minima are there -> winners, their names, push of the winner slab
@@ -587,17 +574,24 @@ static void shard_phase2(ShardOp &op) {
     kxpu_table *t = op.t;
     const XLayout &L = layout(op);
     uint8_t *mine = my_region(op);
+    WaitSpec ws{nullptr, x->nranks, op.epoch, x->scratch + 8};
     if (op.nccl) {
         unsigned long long *a = reinterpret_cast<unsigned long long *>(mine + L.o_a[0]);
         const int nrc = g_nccl.all_reduce(a, a, (size_t)A_WORDS, NCCL_UINT64, NCCL_MIN, ctx->nccl_comm, ctx->stream);
         if (nrc != 0) { nccl_fail(op, "ncclAllReduce(min)", nrc); return; }
     } else {
-        wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(mine + flag_off(0, op.b, 0)), x->nranks, op.epoch, x->scratch + 8);
-        KX_LAUNCHED(ctx);
+        ws.flags = reinterpret_cast<const uint32_t *>(mine + flag_off(0, op.b, 0));
+        if (!x->fuse_waits) {
+            wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(ws);
+            KX_LAUNCHED(ctx);
+            ws.flags = nullptr;
+        }
     }
+    g_trace.mark(3, ctx->stream);
     const unsigned long long *a = reinterpret_cast<const unsigned long long *>(mine + L.o_a[op.b]);
-    op.rc = kx_launch_finalize(ctx, t, op.a.d_text, op.a.n, op.a.base, a, a + A_TRUNC);
+    op.rc = kx_launch_finalize(ctx, t, op.a.d_text, op.a.n, op.a.base, a, a + A_TRUNC, &ws);
     if (op.rc != KXPU_OK) return;
+    g_trace.mark(4, ctx->stream);
     XbParams P;
     memset(&P, 0, sizeof P);
     if (op.nccl) { P.tg.n = 1; P.tg.region[0] = x->send_slab; P.o_slab = 0; P.rows_cap = x->scaps.rows; P.blob_cap = x->scaps.blob; }
@@ -607,6 +601,7 @@ static void shard_phase2(ShardOp &op) {
     P.row_line = t->row_line; P.row_anchor = t->row_anchor; P.blob = t->blob; P.done = x->scratch + 1;
     xb_push_kernel<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(P);
     KX_LAUNCHED(ctx);
+    g_trace.mark(5, ctx->stream);
 }
 
 // phase 3: winners of all ranks -> my table; join of my key slice, results to every rank
@@ -617,15 +612,22 @@ static void shard_phase3(ShardOp &op) {
     kxpu_table *t = op.t;
     const XLayout &L = layout(op);
     uint8_t *mine = my_region(op);
+    WaitSpec ws{nullptr, x->nranks, op.epoch, x->scratch + 8};
     if (op.nccl) {
         const int nrc = g_nccl.all_gather(x->send_slab, mine + L.o_slab[0], L.slab_stride, NCCL_UINT8, ctx->nccl_comm, ctx->stream);
         if (nrc != 0) { nccl_fail(op, "ncclAllGather(winner slabs)", nrc); return; }
     } else {
-        wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(mine + flag_off(1, op.b, 0)), x->nranks, op.epoch, x->scratch + 8);
-        KX_LAUNCHED(ctx);
+        ws.flags = reinterpret_cast<const uint32_t *>(mine + flag_off(1, op.b, 0));
+        if (!x->fuse_waits) {
+            wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(ws);
+            KX_LAUNCHED(ctx);
+            ws.flags = nullptr;
+        }
     }
+    g_trace.mark(6, ctx->stream);
     MergeParams M;
     memset(&M, 0, sizeof M);
+    M.wait = ws;
     M.slabs = mine + L.o_slab[op.b]; M.stride = L.slab_stride; M.R = x->nranks;
     M.slab_rows_cap = op.nccl ? x->scaps.rows : x->caps.rows;
     M.a = reinterpret_cast<const unsigned long long *>(mine + L.o_a[op.b]);
@@ -635,6 +637,7 @@ static void shard_phase3(ShardOp &op) {
     merge_kernel<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(M);
     KX_LAUNCHED(ctx);
     if (ctx->stage_timing) { cudaEventRecord(ctx->ev[2 * KXPU_T_MERGE + 1], ctx->stream); ctx->ev_used[KXPU_T_MERGE] = true; }
+    g_trace.mark(7, ctx->stream);
     if (op.a.nq_total == 0) return;
     KxTimer tm(ctx, KXPU_T_LOOKUP);
     if (op.nccl) {
@@ -651,6 +654,7 @@ static void shard_phase3(ShardOp &op) {
     blocks = std::min<size_t>(blocks, (size_t)ctx->sm_count * 16);
     join_gather_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(J);
     KX_LAUNCHED(ctx);
+    g_trace.mark(8, ctx->stream);
 }
 
 // phase 4: everybody's hits have landed -> caller's buffer; counters to the host
@@ -665,12 +669,28 @@ static void shard_phase4(ShardOp &op) {
             const int nrc = g_nccl.all_gather(op.a.d_rows_all + op.a.key_offset, op.a.d_rows_all, op.a.nq * 4, NCCL_UINT8, ctx->nccl_comm, ctx->stream);
             if (nrc != 0) { nccl_fail(op, "ncclAllGather(hits)", nrc); return; }
         } else {
-            wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(mine + flag_off(2, op.b, 0)), x->nranks, op.epoch, x->scratch + 8);
-            KX_LAUNCHED(ctx);
-            if (op.a.d_rows_all)
-                cudaMemcpyAsync(op.a.d_rows_all, mine + L.o_res[op.b], op.a.nq_total * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+            WaitSpec ws{reinterpret_cast<const uint32_t *>(mine + flag_off(2, op.b, 0)), x->nranks, op.epoch, x->scratch + 8};
+            if (!x->fuse_waits || !op.a.d_rows_all) {
+                wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(ws);
+                KX_LAUNCHED(ctx);
+                ws.flags = nullptr;
+            }
+            if (op.a.d_rows_all) {
+                const int32_t *src = reinterpret_cast<const int32_t *>(mine + L.o_res[op.b]);
+                if ((reinterpret_cast<uintptr_t>(op.a.d_rows_all) & 15u) == 0) {
+                    const size_t n16 = op.a.nq_total / 4;
+                    gather_copy_kernel<<<(unsigned)std::min<size_t>(std::max<size_t>((n16 + 255) / 256, 1), 2u * ctx->sm_count), 256, 0, ctx->stream>>>(
+                        ws, reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(op.a.d_rows_all), n16, src + n16 * 4,
+                        op.a.d_rows_all + n16 * 4, (uint32_t)(op.a.nq_total & 3));
+                    KX_LAUNCHED(ctx);
+                } else {
+                    if (ws.flags) { wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(ws); KX_LAUNCHED(ctx); }
+                    cudaMemcpyAsync(op.a.d_rows_all, src, op.a.nq_total * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+                }
+            }
         }
     }
+    g_trace.mark(9, ctx->stream);
     cudaMemcpyAsync(ctx->h_ctl, op.t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (!op.nccl) cudaMemcpyAsync(ctx->h_ctl + 32, x->scratch + 8, 4, cudaMemcpyDeviceToHost, ctx->stream);
 }
@@ -700,6 +720,7 @@ static int shard_complete(ShardOp &op, kxpu_table **out, int32_t *rc_out) {
         x->broken = true;
         return fail(KXPU_E_CUDA);
     }
+    if (op.a.nq_total && x->ipc) g_trace.report(x->rank, x->nranks);
     const uint32_t *h = ctx->h_ctl;
     const uint32_t st = h[KX_C_XSTATUS];
     if ((st & 0x80000000u) || (!op.nccl && h[32])) {
@@ -710,7 +731,7 @@ static int shard_complete(ShardOp &op, kxpu_table **out, int32_t *rc_out) {
     }
     kxpu_table *t = op.t;
     const uint32_t total_rows = h[KX_C_XROWS], total_blob = h[KX_C_XBLOB], maxkeys = h[KX_C_XMAXKEYS];
-    const bool grow_cap = (st & XS_GROW) || total_rows + maxkeys > t->dev.max_keys || total_rows > t->rows_cap;
+    const bool grow_cap = (st & XS_GROW) || total_rows + maxkeys > merged_key_limit(t->cap) || total_rows > t->rows_cap;
     const bool grow_blob = (st & XS_GROW_BLOB) || total_blob > t->blob_cap;
     const bool need_trunc = (st & XS_NEED_TRUNC) != 0;
     const bool slab_over = (st & XS_SLAB_OVERFLOW) != 0;
@@ -719,7 +740,7 @@ static int shard_complete(ShardOp &op, kxpu_table **out, int32_t *rc_out) {
         op.t = nullptr;
         if (grow_cap) {
             uint32_t cap = x->x_cap;
-            if (!kx_grow_cap(&cap, (size_t)op.a.n * (size_t)x->nranks)) { *rc_out = KXPU_E_CAPACITY; return SH_FAIL; }
+            if (!kx_grow_cap(&cap, (st & XS_FULL) != 0)) { *rc_out = KXPU_E_CAPACITY; return SH_FAIL; }
             x->x_cap = cap;
         }
         if (grow_blob) {
@@ -912,6 +933,10 @@ extern "C" int32_t kxpu_ctx_create_multi(const int32_t *ordinals, int32_t n, kxp
             for (int j = 0; j < n; j++) x->peer[j] = m->ctx[j]->xch->local;  // direct pointers: one address space
             x->p2p = true;
             x->ipc = false;
+            bool distinct = true;
+            for (int a = 0; a < n; a++)
+                for (int b2 = a + 1; b2 < n; b2++) distinct = distinct && m->ctx[a]->device != m->ctx[b2]->device;
+            x->fuse_waits = distinct;
         }
         for (int i = 0; i < n; i++) m->ctx[i]->multi = m;
         *out = m;

@@ -1,0 +1,98 @@
+// exchange.cuh -- device-side pieces of the sharded load's exchange that ride on kernels of the local
+// pipeline (comm.cu owns the protocol): the phase-A push, run by the LAST CTA of the resolve kernel,
+// and the flag wait that a consumer kernel can run in its prologue.
+#pragma once
+#include "common.cuh"
+#include "table.cuh"
+
+namespace kxx {
+
+constexpr uint32_t XS_GROW = 1u;           // a rank's table overflowed / is too full
+constexpr uint32_t XS_NEED_TRUNC = 2u;     // a rank saw a possible >= 64 KiB line: run again with exact cut-offs
+constexpr uint32_t XS_SLAB_OVERFLOW = 4u;  // a rank's winners outgrow the slab
+constexpr uint32_t XS_GROW_BLOB = 8u;      // a rank's name blob is too small
+constexpr uint32_t XS_FULL = 16u;          // a rank's table ran completely full (its key count is unknown): grow faster
+constexpr int XS_BITS = 5;
+
+constexpr int A_TRUNC = 65536;    // phase-A block: u64 [65536] vendor_first | trunc | XS_BITS status words | pad
+constexpr int A_STATUS0 = 65537;  // status bit k is set iff word A_STATUS0 + k == 0 (so that min all-reduces it)
+constexpr int A_WORDS = 65536 + 8;
+
+struct Targets {  // where a push goes: every rank's region (peer memory) or this rank's staging region (NCCL)
+    uint8_t *region[KX_MAX_RANKS];
+    int n;
+};
+
+struct XaParams {
+    Targets tg;
+    uint8_t *mine;         // my region (the next buffer's phase-A block is cleared here)
+    size_t o_a, o_a_next;  // phase-A block of this / the next epoch inside a region
+    int clear_next;
+    size_t o_flag;         // my phase-A flag inside a region (peer transport)
+    int raise_flags;
+    uint32_t epoch;
+    const unsigned long long *vendor_first, *trunc;
+    const uint32_t *counters;
+    uint32_t max_keys;
+    int have_trunc;
+};
+
+// Phase A: vendor_first / cut-off / status of this shard, min-reduced into every rank's region
+// (atomicMin over NVLink for the ~2 400 vendor ids a shard of pci.ids holds), then this rank's flag.
+// vendor_first is final before the last resolve kernel starts, so ALL its threads share the 65536
+// entries (xa_push_slice); cut-off, status and the flags wait for the CTA that finishes last
+// (xa_finish, thread 0 of that CTA, after every CTA's fence + counter).
+__device__ __forceinline__ void xa_push_slice(const XaParams &P, uint32_t gtid, uint32_t gthreads) {
+    unsigned long long *nx = reinterpret_cast<unsigned long long *>(P.mine + P.o_a_next);
+    for (uint32_t v = gtid; v < 65536u; v += gthreads) {
+        const unsigned long long f = P.vendor_first[v];
+        if (P.clear_next) nx[v] = KX_NO_OFF;
+        if (f != KX_NO_OFF)
+            for (int q = 0; q < P.tg.n; q++) atomicMin(reinterpret_cast<unsigned long long *>(P.tg.region[q] + P.o_a) + v, f);
+    }
+    if (P.clear_next && gtid < (uint32_t)(A_WORDS - 65536)) nx[65536 + gtid] = KX_NO_OFF;
+}
+__device__ __forceinline__ void xa_finish(const XaParams &P) {
+    const unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(P.trunc);
+    const volatile uint32_t *c = P.counters;
+    uint32_t st = 0;
+    if (c[KX_C_OVERFLOW]) st |= XS_GROW | XS_FULL;
+    if (c[KX_C_NKEYS] > P.max_keys) st |= XS_GROW;
+    if (c[KX_C_LONGLINE_HINT] && !P.have_trunc) st |= XS_NEED_TRUNC;
+    for (int q = 0; q < P.tg.n; q++) {
+        unsigned long long *a = reinterpret_cast<unsigned long long *>(P.tg.region[q] + P.o_a);
+        if (t != KX_NO_OFF) atomicMin(a + A_TRUNC, t);
+        for (int k = 0; k < XS_BITS; k++)
+            if ((st >> k) & 1u) atomicMin(a + A_STATUS0 + k, 0ull);
+    }
+    __threadfence_system();
+    if (P.raise_flags)
+        for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[q] + P.o_flag) = P.epoch;
+    __threadfence_system();
+}
+
+// Flags of one phase: lane q of the calling warp waits for rank q's flag of this epoch (~4 s time-out).
+struct WaitSpec {
+    const uint32_t *flags;  // nullptr: nothing to wait for
+    int nranks;
+    uint32_t epoch;
+    uint32_t *timeout_flag;
+};
+__device__ __forceinline__ void wait_flags_lane(const WaitSpec &W, int q) {
+    if (q < W.nranks) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<const volatile uint32_t *>(&W.flags[q]) != W.epoch) {
+            __nanosleep(64);
+            if (clock64() - t0 > 8000000000ll) { *W.timeout_flag = 1u; break; }  // a peer died or the ranks lost step
+        }
+    }
+    __threadfence_system();
+}
+// prologue of a consumer kernel (every CTA): the first warp waits, the barrier releases the others
+__device__ __forceinline__ void wait_flags_cta(const WaitSpec &W) {
+    if (W.flags == nullptr) return;
+    if (threadIdx.x < 32) wait_flags_lane(W, (int)threadIdx.x);
+    __syncthreads();
+}
+
+}  // namespace kxx

@@ -1,6 +1,7 @@
 // finalize.cuh -- the kernels behind the parse: bufio.ErrTooLong cut-off, validity + name
 // sanitiser (K4, device_plugin.go:241-251), batched join (K3) and name gather.
 #pragma once
+#include "exchange.cuh"
 #include "parse_common.cuh"
 
 namespace kxparse {
@@ -114,6 +115,7 @@ struct FinalizeParams {
     uint32_t *sel;  // [cap+1] valid slots (stage 1 -> stage 2)
     uint8_t *blob;
     uint32_t blob_cap;
+    kxx::WaitSpec wait;  // sharded load: the all-reduced minima are complete when these flags are up
 };
 
 // Stage 1, one thread per table slot: validity; valid slots are compacted into F.sel.
@@ -121,6 +123,7 @@ struct FinalizeParams {
 // for.  When the parse raised the long-line hint and the cut-off is not there yet, every block
 // leaves (the test does not depend on what block 0 writes) and the host finalizes again.
 __global__ void __launch_bounds__(256) finalize_select_kernel(const FinalizeParams F) {
+    kxx::wait_flags_cta(F.wait);
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (F.tab.counters[KX_C_LONGLINE_HINT] != 0u && F.tab.counters[KX_C_NEED_TRUNC] != 1u) {
         if (slot == 0) F.tab.counters[KX_C_NEED_TRUNC] = 2u;
@@ -144,110 +147,115 @@ __global__ void __launch_bounds__(256) finalize_select_kernel(const FinalizePara
 }
 
 // Stage 2, one warp per selected slot (row handle = index in F.sel): sanitised name into the
-// blob.  Blob space is claimed once per CTA (8 names) to keep the cursor atomic cheap.
+// blob.  Persistent grid: a CTA takes groups of 8 selected slots until the (device-side) count is
+// used up, so a load that selects nothing costs one wave of CTAs that read the count and leave.
+// Blob space is claimed once per group (8 names) to keep the cursor atomic cheap.
 __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const FinalizeParams F) {
     __shared__ uint8_t s_buf[FIN_WARPS][NAME_BUF + 32];
     __shared__ uint32_t s_len[FIN_WARPS];
     __shared__ uint32_t s_base;
     const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5;
     const uint32_t nsel = F.tab.counters[KX_C_NSEL];
-    const uint32_t si = blockIdx.x * FIN_WARPS + wl;
-    if (blockIdx.x * FIN_WARPS >= nsel) return;  // whole CTA idle
-    const bool active = si < nsel;
-    uint32_t slot = 0, key = 0, len = 0, start = 0, end = 0, out_len = 0;
-    unsigned long long line = 0, anchor = 0, rs = 0;
-    bool fast = false;
     uint8_t *buf = s_buf[wl];
-    if (active) {
-        slot = F.sel[si];
-        line = F.tab.slots[slot].min_line;
-        key = slot == F.tab.cap ? KX_EMPTY_KEY : F.tab.slots[slot].key;
-        anchor = F.tab.slots[slot].min_anchor;
-        rs = line - F.base + 5ull;  // rest of the line after "\t" + 4 hex digits
-        bool found = false;
-        for (uint32_t o = 0; o < (uint32_t)NAME_BUF + 32u && !found; o += 128u) {
-            // 128 bytes per step: most names end inside the first one
-            uint32_t nlm[4];
+    for (uint32_t g0 = blockIdx.x * FIN_WARPS; g0 < nsel; g0 += gridDim.x * FIN_WARPS) {
+        const uint32_t si = g0 + wl;
+        const bool active = si < nsel;
+        uint32_t slot = 0, key = 0, len = 0, start = 0, end = 0, out_len = 0;
+        unsigned long long line = 0, anchor = 0, rs = 0;
+        bool fast = false;
+        if (active) {
+            slot = F.sel[si];
+            line = F.tab.slots[slot].min_line;
+            key = slot == F.tab.cap ? KX_EMPTY_KEY : F.tab.slots[slot].key;
+            anchor = F.tab.slots[slot].min_anchor;
+            rs = line - F.base + 5ull;  // rest of the line after "\t" + 4 hex digits
+            bool found = false;
+            for (uint32_t o = 0; o < (uint32_t)NAME_BUF + 32u && !found; o += 128u) {
+                // 128 bytes per step: most names end inside the first one
+                uint32_t nlm[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned long long pos = rs + o + 32u * k + lane;
-                const uint32_t c = pos < F.n ? F.text[pos] : 0x0au;  // EOF terminates the last line
-                if (o + 32u * k < (uint32_t)NAME_BUF + 32u) buf[o + 32u * k + lane] = (uint8_t)c;
-                nlm[k] = __ballot_sync(0xffffffffu, c == 0x0au);
+                for (int k = 0; k < 4; k++) {
+                    const unsigned long long pos = rs + o + 32u * k + lane;
+                    const uint32_t c = pos < F.n ? F.text[pos] : 0x0au;  // EOF terminates the last line
+                    if (o + 32u * k < (uint32_t)NAME_BUF + 32u) buf[o + 32u * k + lane] = (uint8_t)c;
+                    nlm[k] = __ballot_sync(0xffffffffu, c == 0x0au);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (!found && nlm[k]) { len = o + 32u * k + (uint32_t)__ffs((int)nlm[k]) - 1u; found = true; }
             }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (!found && nlm[k]) { len = o + 32u * k + (uint32_t)__ffs((int)nlm[k]) - 1u; found = true; }
+            __syncwarp();
+            fast = found && len <= (uint32_t)NAME_BUF;
+            if (fast) {
+                if (len > 0 && buf[len - 1] == 0x0du) len--;  // bufio.ScanLines drops one trailing CR
+                if (lane == 0) trim_space(buf, len, start, end);
+                start = __shfl_sync(0xffffffffu, start, 0);
+                end = __shfl_sync(0xffffffffu, end, 0);
+                for (uint32_t o = start; o < end; o += 32u) {
+                    uint32_t i = o + lane;
+                    uint32_t ch = i < end ? sanitise_byte(buf, i, start, end) : 0u;
+                    out_len += (uint32_t)__popc(__ballot_sync(0xffffffffu, ch != 0u));
+                }
+            } else {
+                // slow path: a name longer than the staging buffer (never in pci.ids): lane 0, serial,
+                // straight from global memory.
+                if (lane == 0) {
+                    const uint8_t *g = F.text + rs;
+                    unsigned long long avail = F.n - rs, l = 0;
+                    while (l < avail && g[l] != 0x0au) l++;
+                    len = (uint32_t)l;
+                    if (len > 0 && g[len - 1] == 0x0du) len--;
+                    trim_space(g, len, start, end);
+                    for (uint32_t i = start; i < end; i++) out_len += sanitise_byte(g, i, start, end) != 0u;
+                }
+                out_len = __shfl_sync(0xffffffffu, out_len, 0);
+                start = __shfl_sync(0xffffffffu, start, 0);
+                end = __shfl_sync(0xffffffffu, end, 0);
+            }
         }
-        __syncwarp();
-        fast = found && len <= (uint32_t)NAME_BUF;
-        if (fast) {
-            if (len > 0 && buf[len - 1] == 0x0du) len--;  // bufio.ScanLines drops one trailing CR
-            if (lane == 0) trim_space(buf, len, start, end);
-            start = __shfl_sync(0xffffffffu, start, 0);
-            end = __shfl_sync(0xffffffffu, end, 0);
-            for (uint32_t o = start; o < end; o += 32u) {
-                uint32_t i = o + lane;
-                uint32_t ch = i < end ? sanitise_byte(buf, i, start, end) : 0u;
-                out_len += (uint32_t)__popc(__ballot_sync(0xffffffffu, ch != 0u));
+        if (lane == 0) s_len[wl] = out_len;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int k = 0; k < FIN_WARPS; k++) tot += s_len[k];
+            uint32_t base = tot ? atomicAdd(&F.tab.counters[KX_C_BLOB_CURSOR], tot) : 0u;
+            if (base + tot > F.blob_cap) { F.tab.counters[KX_C_BLOB_OVERFLOW] = 1u; base = 0xFFFFFFFFu; }
+            s_base = base;
+        }
+        __syncthreads();
+        if (active) {
+            uint32_t out_off = s_base;
+            const bool room = out_off != 0xFFFFFFFFu;
+            for (uint32_t k = 0; k < wl; k++) out_off += s_len[k];
+            if (room) {
+                if (fast) {
+                    uint32_t wr = out_off;
+                    for (uint32_t o = start; o < end; o += 32u) {
+                        uint32_t i = o + lane;
+                        uint32_t ch = i < end ? sanitise_byte(buf, i, start, end) : 0u;
+                        uint32_t bm = __ballot_sync(0xffffffffu, ch != 0u);
+                        if (ch) F.blob[wr + (uint32_t)__popc(bm & ((1u << lane) - 1u))] = (uint8_t)ch;
+                        wr += (uint32_t)__popc(bm);
+                    }
+                } else if (lane == 0) {
+                    const uint8_t *g = F.text + rs;
+                    uint32_t wr = out_off;
+                    for (uint32_t i = start; i < end; i++) {
+                        uint32_t ch = sanitise_byte(g, i, start, end);
+                        if (ch) F.blob[wr++] = (uint8_t)ch;
+                    }
+                }
             }
-        } else {
-            // slow path: a name longer than the staging buffer (never in pci.ids): lane 0, serial,
-            // straight from global memory.
             if (lane == 0) {
-                const uint8_t *g = F.text + rs;
-                unsigned long long avail = F.n - rs, l = 0;
-                while (l < avail && g[l] != 0x0au) l++;
-                len = (uint32_t)l;
-                if (len > 0 && g[len - 1] == 0x0du) len--;
-                trim_space(g, len, start, end);
-                for (uint32_t i = start; i < end; i++) out_len += sanitise_byte(g, i, start, end) != 0u;
-            }
-            out_len = __shfl_sync(0xffffffffu, out_len, 0);
-            start = __shfl_sync(0xffffffffu, start, 0);
-            end = __shfl_sync(0xffffffffu, end, 0);
-        }
-    }
-    if (lane == 0) s_len[wl] = out_len;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int k = 0; k < FIN_WARPS; k++) tot += s_len[k];
-        uint32_t base = tot ? atomicAdd(&F.tab.counters[KX_C_BLOB_CURSOR], tot) : 0u;
-        if (base + tot > F.blob_cap) { F.tab.counters[KX_C_BLOB_OVERFLOW] = 1u; base = 0xFFFFFFFFu; }
-        s_base = base;
-    }
-    __syncthreads();
-    if (!active) return;
-    uint32_t out_off = s_base;
-    const bool room = out_off != 0xFFFFFFFFu;
-    for (uint32_t k = 0; k < wl; k++) out_off += s_len[k];
-    if (room) {
-        if (fast) {
-            uint32_t wr = out_off;
-            for (uint32_t o = start; o < end; o += 32u) {
-                uint32_t i = o + lane;
-                uint32_t ch = i < end ? sanitise_byte(buf, i, start, end) : 0u;
-                uint32_t bm = __ballot_sync(0xffffffffu, ch != 0u);
-                if (ch) F.blob[wr + (uint32_t)__popc(bm & ((1u << lane) - 1u))] = (uint8_t)ch;
-                wr += (uint32_t)__popc(bm);
-            }
-        } else if (lane == 0) {
-            const uint8_t *g = F.text + rs;
-            uint32_t wr = out_off;
-            for (uint32_t i = start; i < end; i++) {
-                uint32_t ch = sanitise_byte(g, i, start, end);
-                if (ch) F.blob[wr++] = (uint8_t)ch;
+                F.tab.slots[slot].row = (int32_t)si;
+                F.row_key[si] = key;
+                F.row_line[si] = line;
+                F.row_anchor[si] = anchor;
+                F.row_name_off[si] = room ? out_off : 0u;
+                F.row_name_len[si] = room ? out_len : 0u;
             }
         }
-    }
-    if (lane == 0) {
-        F.tab.slots[slot].row = (int32_t)si;
-        F.row_key[si] = key;
-        F.row_line[si] = line;
-        F.row_anchor[si] = anchor;
-        F.row_name_off[si] = room ? out_off : 0u;
-        F.row_name_len[si] = room ? out_len : 0u;
+        __syncthreads();  // s_len / s_base / the staging buffers are reused by the next group
     }
 }
 

@@ -2,6 +2,7 @@
 // comm.cu (sharded load).  Not part of the ABI.
 #pragma once
 #include "common.cuh"
+#include "exchange.cuh"
 #include "table.cuh"
 
 struct kxpu_table {
@@ -33,13 +34,18 @@ int32_t kx_table_acquire(kxpu_ctx *ctx, uint32_t cap, uint32_t blob_cap, uint32_
 void kx_table_release(kxpu_ctx *ctx, kxpu_table *t);
 uint32_t kx_initial_blob_cap(kxpu_ctx *ctx, size_t n);
 // parse + resolve kernels of d_text[0..n) (global offsets base + local) into t
+// xa (may be null): phase-A push of the sharded load, run by the last CTA of the resolve kernel
+struct KxXaHook {
+    kxx::XaParams p;
+    uint32_t *done;
+};
 int32_t kx_launch_parse(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base,
-                        unsigned long long carry_in);
+                        unsigned long long carry_in, const KxXaHook *xa);
 int32_t kx_launch_trunc(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base);
 // validity + names; vendor_first / trunc: what validity is judged against (nullptr: the table's own)
 int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base,
-                           const unsigned long long *vendor_first, const unsigned long long *trunc);
+                           const unsigned long long *vendor_first, const unsigned long long *trunc, const kxx::WaitSpec *wait);
 int32_t kx_launch_lookup(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *d_keys, size_t n, int32_t *d_rows);
 // growth policy shared by the single and the sharded load; returns false when the limit is reached
-bool kx_grow_cap(uint32_t *cap, size_t n_text);
+bool kx_grow_cap(uint32_t *cap, bool table_full);
 void kx_note_table_size(kxpu_ctx *ctx, uint32_t nkeys, uint32_t blob_used, uint32_t blob_cap);

@@ -22,6 +22,7 @@ constexpr unsigned long long ST_MASK = 3ull << 62;
 constexpr unsigned long long CV_HAS_TOP = 1ull << 61;
 constexpr unsigned long long CV_VOK = 1ull << 60;
 constexpr unsigned long long CV_ANCHOR_MASK = (1ull << 44) - 1;
+constexpr uint32_t KX_MAX_PROBE = 1024;  // longest probe run a table within its load limit can show (inserts give up beyond)
 constexpr uint32_t P_NONE = 0xFFFFFFFFu;  // packed top info: [31] alive, [30:15] vendor, [14:0] position
 // carry along a range (one register): [31] known, [30] top-level line seen, [29] alive vendor line,
 // [27:12] vendor, [11:0] position in its chunk
@@ -82,9 +83,11 @@ __device__ __forceinline__ bool hex4_swar(uint32_t x, uint32_t &val) {
 }
 
 // Fold one device line into the table (first occurrence wins).  The slot is one 32-byte
-// sector: key and min_line arrive with one load.
+// sector: key and min_line arrive with one load.  `fresh` counts the slots this thread claimed:
+// the caller adds it to counters[KX_C_NKEYS] once per warp and chunk (one same-address atomic per
+// key would serialise in L2 when every block is a first occurrence).
 __device__ __forceinline__ void table_fold(const KxTableDev &tb, uint32_t key, unsigned long long line_g,
-                                           unsigned long long anchor_g) {
+                                           unsigned long long anchor_g, uint32_t &fresh_cnt) {
     uint32_t slot = key == KX_EMPTY_KEY ? tb.cap : (kx_hash(key) >> tb.shift);
     uint4 head = __ldcg(reinterpret_cast<const uint4 *>(&tb.slots[slot]));  // key, row, min_line (L2: where the atomics live)
     uint32_t k = head.x;
@@ -96,15 +99,16 @@ __device__ __forceinline__ void table_fold(const KxTableDev &tb, uint32_t key, u
             if (k == KX_EMPTY_KEY) {
                 uint32_t old = atomicCAS(&tb.slots[slot].key, KX_EMPTY_KEY, key);
                 if (old == KX_EMPTY_KEY) {
-                    // the count is only compared with max_keys by the host (growth): fire and forget
-                    atomicAdd(&tb.counters[KX_C_NKEYS], 1u);
+                    fresh_cnt++;
                     fresh = true;
                     break;
                 }
                 if (old == key) break;
             }
             slot = (slot + 1) & (tb.cap - 1);
-            if (++step >= tb.cap) { tb.counters[KX_C_OVERFLOW] = 1u; return; }
+            // below the 50 % load limit a probe run of KX_MAX_PROBE is out of the question: the table is
+            // (over)full, the host grows it and parses again -- do not crawl through a full table
+            if (++step >= KX_MAX_PROBE) { tb.counters[KX_C_OVERFLOW] = 1u; return; }
             k = __ldcg(&tb.slots[slot].key);
             if (k == key) break;
         }
@@ -130,16 +134,17 @@ __device__ __forceinline__ int32_t table_probe(const KxSlot *__restrict__ slots,
     return -1;
 }
 
-// find or claim the slot of `key` while the table is being built (0xffffffff: table full)
-__device__ __forceinline__ uint32_t table_claim(const KxTableDev &tb, uint32_t key) {
+// find or claim the slot of `key` while the table is being built (0xffffffff: table full);
+// fresh_cnt as in table_fold
+__device__ __forceinline__ uint32_t table_claim(const KxTableDev &tb, uint32_t key, uint32_t &fresh_cnt) {
     if (key == KX_EMPTY_KEY) return tb.cap;
     uint32_t slot = kx_hash(key) >> tb.shift;
-    for (uint32_t step = 0; step < tb.cap; step++) {
+    for (uint32_t step = 0; step < KX_MAX_PROBE; step++) {
         const uint32_t k = __ldcg(&tb.slots[slot].key);
         if (k == key) return slot;
         if (k == KX_EMPTY_KEY) {
             const uint32_t old = atomicCAS(&tb.slots[slot].key, KX_EMPTY_KEY, key);
-            if (old == KX_EMPTY_KEY) { atomicAdd(&tb.counters[KX_C_NKEYS], 1u); return slot; }
+            if (old == KX_EMPTY_KEY) { fresh_cnt++; return slot; }
             if (old == key) return slot;
         }
         slot = (slot + 1) & (tb.cap - 1);
@@ -275,14 +280,23 @@ __device__ __forceinline__ void chunk_masks(uint32_t st, uint32_t lane, uint32_t
 // the alive top-level line (key_hi, anchor): parse the id, fold.  Per-lane loop: only blocks of
 // a first-seen vendor id get here.
 __device__ __forceinline__ void fold_lines(const KxTableDev &tab, uint32_t st, unsigned long long cbase, uint32_t m, uint32_t pbase,
-                                           uint32_t key_hi, unsigned long long anchor) {
+                                           uint32_t key_hi, unsigned long long anchor, uint32_t &fresh_cnt) {
     while (m) {
         const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
         m &= m - 1u;
         const uint32_t p = pbase + b;
         uint32_t dv;
-        if (hex4_swar(lds32_unaligned(st + p + 1u), dv)) table_fold(tab, key_hi | dv, cbase + p, anchor);
+        if (hex4_swar(lds32_unaligned(st + p + 1u), dv)) table_fold(tab, key_hi | dv, cbase + p, anchor, fresh_cnt);
     }
 }
 
+}  // namespace kxparse
+
+namespace kxparse {
+// one atomic per warp for the keys its lanes claimed (all 32 lanes must call)
+__device__ __forceinline__ void flush_fresh(const KxTableDev &tb, uint32_t &fresh_cnt) {
+    const uint32_t tot = __reduce_add_sync(0xffffffffu, fresh_cnt);
+    if (tot && (threadIdx.x & 31u) == 0u) atomicAdd(&tb.counters[KX_C_NKEYS], tot);
+    fresh_cnt = 0;
+}
 }  // namespace kxparse

@@ -24,6 +24,7 @@
 // Earlier generations (CTA-tiled, per-chunk look-back, super-chunks, CTA barrier per 16 KiB) are
 // in the git history and in profiles/r01_parse_v*; DESIGN.md has the numbers.
 #pragma once
+#include "exchange.cuh"
 #include "parse_common.cuh"
 
 namespace kxparse5 {
@@ -52,6 +53,10 @@ struct Params5 {
     uint32_t *tasks;                  // [num_chunks] resolve: chunks to stage again, count in counters[KX_C_DEFER]
     KxTableDev tab;
     unsigned long long carry_in;
+    // sharded load: the CTA of the last resolve kernel that finishes last pushes this shard's minima (phase A)
+    int xa_on;
+    uint32_t *xa_done;
+    kxx::XaParams xa;
 };
 
 
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
     bool staged = false;  // the first chunks of the coming range are already on their way
 
     uint32_t phase_bits = 0, s = 0;
+    uint32_t nfresh = 0;  // table slots this lane claimed in the current chunk (flushed once per warp and chunk)
     for (;;) {
         // ticket of the next range, drawn one range early; looked at (shuffled) late in this range
         uint32_t tk2 = 0, r_next = 0xffffffffu;
@@ -235,6 +241,9 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
                 uint32_t kh[2];
                 kh[0] = th[0] | devs_of(st + lane * 32u + 1u, nl[0] & ~th[0]);
                 kh[1] = th[1] | devs_of(st + (uint32_t)HALF + lane * 32u + 1u, nl[1] & ~th[1]);
+                // the table ran full (the host grows it and parses again): fold nothing more
+                const bool table_dead = *reinterpret_cast<volatile uint32_t *>(&P.tab.counters[KX_C_OVERFLOW]) != 0u;
+                if (table_dead) { kh[0] = th[0]; kh[1] = th[1]; }
 
                 // the shard starts with a line start at p = 0 (no newline before it)
                 uint32_t base_info = P_NONE;  // top-level line in front of the lane windows (only that one)
@@ -253,8 +262,8 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
                     } else if (c0 == (uint32_t)'\t' && c1 != (uint32_t)'\t') {
                         // device line at the very start: governed by the shard's carry-in, which is known
                         uint32_t dv;
-                        if (lane == 0 && (P.carry_in & CV_HAS_TOP) && (P.carry_in & CV_VOK) && hex4_swar(lds32_unaligned(st + 1u), dv))
-                            table_fold(P.tab, (((uint32_t)(P.carry_in >> 44) & 0xffffu) << 16) | dv, cbase, P.carry_in & CV_ANCHOR_MASK);
+                        if (lane == 0 && !table_dead && (P.carry_in & CV_HAS_TOP) && (P.carry_in & CV_VOK) && hex4_swar(lds32_unaligned(st + 1u), dv))
+                            table_fold(P.tab, (((uint32_t)(P.carry_in >> 44) & 0xffffu) << 16) | dv, cbase, P.carry_in & CV_ANCHOR_MASK, nfresh);
                     }
                 }
                 // device lines behind the top-level lines of my windows (alive ones only)
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
                         if (alive) {
                             const uint32_t nxt = rest & (0u - rest);
                             const uint32_t seg = (second ? kh[1] & ~th[1] : kh[0] & ~th[0]) & ~(bit | (bit - 1u)) & (nxt ? nxt - 1u : 0xffffffffu);
-                            fold_lines(P.tab, st, cbase, seg, pbase, val << 16, line_g);
+                            fold_lines(P.tab, st, cbase, seg, pbase, val << 16, line_g, nfresh);
                         }
                         const uint32_t info = (alive ? 0x80000000u : 0u) | ((ok ? val : 0u) << 15) | p;
                         if (second) linfo1 = info; else linfo0 = info;
@@ -296,9 +305,9 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
                 last1 = bal1 ? l1 : last0;
                 // governed by an alive line of an earlier window of this chunk
                 if (cin0 != P_NONE && (cin0 >> 31))
-                    fold_lines(P.tab, st, cbase, pre0, lane * 32u + 1u, ((cin0 >> 15) & 0xffffu) << 16, cbase + (cin0 & 0x7fffu));
+                    fold_lines(P.tab, st, cbase, pre0, lane * 32u + 1u, ((cin0 >> 15) & 0xffffu) << 16, cbase + (cin0 & 0x7fffu), nfresh);
                 if (cin1 != P_NONE && (cin1 >> 31))
-                    fold_lines(P.tab, st, cbase, pre1, (uint32_t)HALF + lane * 32u + 1u, ((cin1 >> 15) & 0xffffu) << 16, cbase + (cin1 & 0x7fffu));
+                    fold_lines(P.tab, st, cbase, pre1, (uint32_t)HALF + lane * 32u + 1u, ((cin1 >> 15) & 0xffffu) << 16, cbase + (cin1 & 0x7fffu), nfresh);
                 // head lines (in front of the chunk's first top-level line): governed by the carry; if
                 // that is not known yet, the resolve kernels look at them
                 const uint32_t hw0 = cin0 == P_NONE ? pre0 : 0u;
@@ -312,10 +321,11 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
                     }
                     // still the first line of its id?
                     if ((hw0 | hw1) != 0u && P.tab.vendor_first[key_hi >> 16] >= anchor) {
-                        fold_lines(P.tab, st, cbase, hw0, lane * 32u + 1u, key_hi, anchor);
-                        fold_lines(P.tab, st, cbase, hw1, (uint32_t)HALF + lane * 32u + 1u, key_hi, anchor);
+                        fold_lines(P.tab, st, cbase, hw0, lane * 32u + 1u, key_hi, anchor, nfresh);
+                        fold_lines(P.tab, st, cbase, hw1, (uint32_t)HALF + lane * 32u + 1u, key_hi, anchor, nfresh);
                     }
                 }
+                flush_fresh(P.tab, nfresh);  // full path only: the branch is warp-uniform (__any_sync above)
             }
             if (last1 != P_NONE) {
                 if (rc_x == 0u) lead = i + 1u;  // chunks 0..i have head lines nobody judged
@@ -427,8 +437,9 @@ __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Pa
     __syncwarp();
     const unsigned long long pol = l2_evict_first_policy();
     const uint32_t n_tasks = P.tab.counters[KX_C_DEFER];
-    uint32_t par = 0;
+    uint32_t par = 0, nfresh = 0;
     for (uint32_t t = blockIdx.x * RES_WARPS + w; t < n_tasks; t += gridDim.x * RES_WARPS) {
+        if (*reinterpret_cast<volatile uint32_t *>(&P.tab.counters[KX_C_OVERFLOW]) != 0u) break;  // table full: the host parses again
         const uint32_t gg = P.tasks[t];
         uint32_t n_rel = CW + 1;
         if (gg < P.tma_limit) {
@@ -453,9 +464,26 @@ __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Pa
         const uint32_t pre0 = kh[0] & ~th[0] & (th[0] ? (th[0] & (0u - th[0])) - 1u : 0xffffffffu);
         const uint32_t pre1 = kh[1] & ~th[1] & (th[1] ? (th[1] & (0u - th[1])) - 1u : 0xffffffffu);
         const unsigned long long cbase = P.base + (unsigned long long)gg * CW;
-        if ((bal0 & lt_mask) == 0u) fold_lines(P.tab, st, cbase, pre0, lane * 32u + 1u, key_hi, anchor);
-        if (bal0 == 0u && (bal1 & lt_mask) == 0u) fold_lines(P.tab, st, cbase, pre1, (uint32_t)HALF + lane * 32u + 1u, key_hi, anchor);
-        __syncwarp();
+        if ((bal0 & lt_mask) == 0u) fold_lines(P.tab, st, cbase, pre0, lane * 32u + 1u, key_hi, anchor, nfresh);
+        if (bal0 == 0u && (bal1 & lt_mask) == 0u) fold_lines(P.tab, st, cbase, pre1, (uint32_t)HALF + lane * 32u + 1u, key_hi, anchor, nfresh);
+        flush_fresh(P.tab, nfresh);
+    }
+    if (P.xa_on) {
+        // phase A of the sharded load rides on this kernel: every CTA pushes its slice of the shard's
+        // vendor minima; the table is final once every CTA is through, the last one adds cut-off and
+        // status and raises the flags (the barrier + thread 0's cumulative system fence order each
+        // CTA's pushes in front of its count)
+        kxx::xa_push_slice(P.xa, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const uint32_t prev = atomicAdd(P.xa_done, 1u);
+            if (prev == gridDim.x - 1u) {
+                *P.xa_done = 0u;
+                __threadfence_system();
+                kxx::xa_finish(P.xa);
+            }
+        }
     }
 }
 

@@ -142,3 +142,50 @@ def cfg5_devices(n=65536):
     devs["iommu_group"] = (1000 + np.arange(n) // 2).astype(np.uint32)
     devs["index"] = np.arange(n, dtype=np.uint64)
     return devs
+
+
+def synthetic_pci_ids(n_vendors, devs_per_vendor, subs_per_dev=1, seed=7, copies=1):
+    """pci.ids-shaped synthetic text WITHOUT replication (north_star's "pci.ids-shaped synthetic text"):
+    n_vendors distinct vendor ids (<= 65536), each with devs_per_vendor distinct device ids and
+    subs_per_dev subsystem lines per device -- every vendor block is a first occurrence, so the parse
+    cannot skip anything ("all-alive" text).  Fixed-width lines (vendor 29 B, device 42 B, subsystem
+    38 B: close to the 38 B mean of the real file).  numpy only; returns a uint8 array."""
+    assert 0 < n_vendors <= 65536 and 0 < devs_per_vendor <= 65536
+    hexd = np.frombuffer(b"0123456789abcdef", np.uint8)
+    rng = np.random.default_rng(seed)
+    v_ids = rng.permutation(65536)[:n_vendors].astype(np.int64)
+    v_ids.sort()  # the real file is sorted by vendor id
+
+    def put_hex4(arr, col, vals):
+        for k in range(4):
+            arr[..., col + k] = hexd[(vals >> (12 - 4 * k)) & 15]
+
+    def put_dec(arr, col, vals, width):
+        for k in range(width):
+            arr[..., col + width - 1 - k] = ord("0") + (vals // 10 ** k) % 10
+
+    vline = np.frombuffer(b"vvvv  Vendor Corp. Nr 00000\n", np.uint8)
+    dline = np.frombuffer(b"\tdddd  Device / Model 00000 [Rev. 000000]\n", np.uint8)
+    sline = np.frombuffer(b"\t\tvvvv dddd  Subsystem board 00000\n", np.uint8)
+    block = len(vline) + devs_per_vendor * (len(dline) + subs_per_dev * len(sline))
+    out = np.empty((n_vendors, block), np.uint8)
+    out[:, :len(vline)] = vline
+    put_hex4(out, 0, v_ids)
+    put_dec(out, 22, v_ids, 5)
+    body = out[:, len(vline):].reshape(n_vendors, devs_per_vendor, len(dline) + subs_per_dev * len(sline))
+    # distinct device ids per vendor: an odd stride walks all 65536 values
+    start = rng.integers(0, 65536, n_vendors)[:, None]
+    stride = (rng.integers(0, 32768, n_vendors)[:, None] * 2 + 1)
+    d_ids = (start + stride * np.arange(devs_per_vendor)[None, :]) & 0xFFFF
+    body[:, :, :len(dline)] = dline
+    put_hex4(body, 1, d_ids)
+    put_dec(body, 22, d_ids, 5)
+    put_dec(body, 34, (d_ids * 7919) % 1000000, 6)
+    for s in range(subs_per_dev):
+        o = len(dline) + s * len(sline)
+        body[:, :, o:o + len(sline)] = sline
+        put_hex4(body, o + 2, np.broadcast_to(v_ids[:, None], d_ids.shape))
+        put_hex4(body, o + 7, (d_ids + s + 1) & 0xFFFF)
+        put_dec(body, o + 29, d_ids, 5)
+    flat = out.reshape(-1)
+    return np.tile(flat, copies) if copies > 1 else flat

@@ -167,3 +167,53 @@ def test_ctx_is_thread_safe(kx, oracle, pci_text):
     assert not errors, errors[:3]
     assert kx.alloc_names(np.arange(64, dtype=np.uint64))[0] == want_names
     tab.free()
+
+
+def test_cdi_emit_tile_boundaries_and_sizing(kx, oracle, workloads):
+    """The emitter works in tiles of 128 devices whose bytes leave shared memory with one bulk store:
+    every count around the tile edges, mixed field widths (so that fragments start at every 16-byte
+    phase), and the two-call sizing protocol."""
+    rng = np.random.default_rng(11)
+    n = 1000
+    devs = workloads.cfg5_devices(n)
+    devs["index"] = rng.integers(0, 2**63, n, dtype=np.uint64) >> rng.integers(0, 63, n).astype(np.uint64)
+    devs["iommu_group"] = (rng.integers(0, 2**32 - 1, n, dtype=np.uint64) >> rng.integers(0, 31, n).astype(np.uint64)).astype(np.uint32)
+    for cnt in [1, 2, 3, 127, 128, 129, 255, 256, 257, 383, 384, 385, 1000]:
+        for fmt in (0, 1):
+            want = oracle.cdi_emit(fmt, devs[:cnt])
+            assert kx.cdi_emit(fmt, devs[:cnt]) == want
+            assert kx.cdi_emit_len(fmt, devs[:cnt]) == len(want)
+
+
+def _rec_strategy():
+    from hypothesis import strategies as st
+    vendor = st.sampled_from([b"0x10de\n", b"0x10de", b"0x10DE\n", b"0x8086\n", b"0x10de\n\n", b"10de\n", b"0x10d\n", b"0x", b"0", b"",
+                              b"\n\n10de\n", b"0x10de\n\0"])
+    device = st.sampled_from([b"0x2330\n", b"0x2331\n", b"0x20b0\n", b"0x2330", b"0x\n", b"0x", b"0", b"0xabcdef", b"0x1\n", b"0x2330\n\n"])
+    driver = st.sampled_from([b"vfio-pci", b"nvidia", b"vfio-pc", b"vfio-pci2", b"", b"Vfio-pci"])  # NUL-padded C strings: no embedded NUL
+    return st.tuples(vendor, device, driver, st.integers(0, 6), st.sampled_from([0, 0, 0, 0, 1, 2, 4, 8, 16, 12]))
+
+
+def test_classify_hypothesis_fuzz(kx, oracle):
+    """Oracle-vs-GPU fuzz of kxpu_classify with hypothesis-generated records: odd id files (short,
+    upper case, extra newlines), near-miss driver names, read-error flags, tiny group universes so
+    that groups interleave and first members fail their device read."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    import kxpu_b200 as K
+    dt = K.binding.DEVREC_DTYPE
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.lists(_rec_strategy(), min_size=0, max_size=300))
+    def run(items):
+        recs = np.zeros(len(items), dtype=dt)
+        for i, (v, d, drv, grp, fl) in enumerate(items):
+            recs["bdf"][i] = b"0000:%02x:%02x.%d" % (i >> 8, (i >> 3) & 31, i & 7)
+            recs["vendor_txt"][i, :len(v[:8])] = np.frombuffer(v[:8], np.uint8)
+            recs["device_txt"][i, :len(d[:8])] = np.frombuffer(d[:8], np.uint8)
+            recs["vendor_len"][i], recs["device_len"][i] = len(v), len(d)
+            recs["driver"][i] = drv
+            recs["iommu_group"][i] = grp
+            recs["flags"][i] = fl
+        assert_classify_equal(kx.classify(recs), oracle.classify(recs))
+        check_classify(kx.classify(recs), recs)
+    run()
