@@ -379,9 +379,11 @@ int32_t kx_launch_parse(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, siz
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kxparse5::parse_kernel_v5, NT, smem);
         if (per_sm < 1) per_sm = 1;
     }
-    // ranges of 8 chunks; shorter ones when the text is too small to give every warp a range
+    // ranges of 8 chunks; shorter ones when the text is too small to give every warp about eight
+    // ranges (with two or three 16 KiB ranges per warp the last wave is half empty, and a range of a
+    // first-seen vendor block costs its warp ~10 us per chunk)
     const uint32_t wave_warps = (uint32_t)per_sm * ctx->sm_count * WARPS;
-    P.rch = std::min<uint32_t>(std::max<uint32_t>(num_chunks / wave_warps, 1u), kxparse5::RCH5_MAX);
+    P.rch = std::min<uint32_t>(std::max<uint32_t>(num_chunks / (wave_warps * 8u), 1u), kxparse5::RCH5_MAX);
     if (ctx->force_rch) P.rch = (uint32_t)ctx->force_rch;
     P.num_ranges = (num_chunks + P.rch - 1) / P.rch;
     P.range_state = t->range_words;                            // [num_ranges]
@@ -418,7 +420,8 @@ int32_t kx_launch_trunc(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, siz
 }
 
 int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base,
-                           const unsigned long long *vendor_first, const unsigned long long *trunc, const kxx::WaitSpec *wait) {
+                           const unsigned long long *vendor_first, const unsigned long long *trunc, const kxx::WaitSpec *wait,
+                           const KxSlabOut *slab) {
     kxparse::FinalizeParams F;
     memset(&F, 0, sizeof F);
     if (wait) F.wait = *wait;
@@ -426,14 +429,18 @@ int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, 
     F.vendor_first = vendor_first ? vendor_first : t->dev.vendor_first;
     F.trunc = trunc ? trunc : t->dev.trunc;
     F.row_key = t->row_key; F.row_line = t->row_line; F.row_anchor = t->row_anchor;
-    F.row_name_off = t->row_name_off; F.row_name_len = t->row_name_len; F.sel = t->sel;
+    F.row_name_off = t->row_name_off; F.row_name_len = t->row_name_len;
     F.blob = t->blob; F.blob_cap = t->blob_cap;
+    if (slab) {
+        F.slab_rows = reinterpret_cast<kxx::SlabRow *>(slab->rows); F.slab_rows_cap = slab->rows_cap;
+        F.blob = slab->blob; F.blob_cap = slab->blob_cap;
+    }
     KxTimer tm(ctx, KXPU_T_FINALIZE);
-    kxparse::finalize_select_kernel<<<(t->cap + 1 + 255) / 256, 256, 0, ctx->stream>>>(F);
-    // one warp per selected slot, persistent grid (the count lives on the device)
-    const unsigned fin_grid = std::min<unsigned>((t->cap + 1 + kxparse::FIN_WARPS - 1) / kxparse::FIN_WARPS, 8u * ctx->sm_count);
-    kxparse::finalize_kernel<<<fin_grid, kxparse::FIN_WARPS * 32, 0, ctx->stream>>>(F);
-    ctx->launches += 2;
+    // validity + names: one warp per SF_BATCH table slots, persistent grid
+    const unsigned batches = (t->cap + 1 + kxparse::SF_BATCH - 1) / kxparse::SF_BATCH;
+    const unsigned grid = std::min<unsigned>((batches + kxparse::SF_WARPS - 1) / kxparse::SF_WARPS, 8u * ctx->sm_count);
+    kxparse::select_finalize_kernel<<<grid, kxparse::SF_WARPS * 32, 0, ctx->stream>>>(F);
+    KX_LAUNCHED(ctx);
     KX_CUDA(ctx, cudaGetLastError());
     return KXPU_OK;
 }
@@ -477,7 +484,7 @@ static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t 
         // a text with a >= 2 KiB stretch without a newline was seen on an earlier attempt: the exact
         // bufio.ErrTooLong cut-off is computed before the finalize
         if (rc == KXPU_OK && have_trunc) rc = kx_launch_trunc(ctx, t, d_text, n, 0);
-        if (rc == KXPU_OK) rc = kx_launch_finalize(ctx, t, d_text, n, 0, nullptr, nullptr, nullptr);
+        if (rc == KXPU_OK) rc = kx_launch_finalize(ctx, t, d_text, n, 0, nullptr, nullptr, nullptr, nullptr);
         // the join does not need anything from the host: enqueue it before the round trip below
         // (it is simply run again if the table has to be rebuilt)
         if (rc == KXPU_OK && join) rc = kx_launch_lookup(ctx, t, join->d_keys, join->n, join->d_rows);

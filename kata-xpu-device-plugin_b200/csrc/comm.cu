@@ -89,16 +89,6 @@ constexpr size_t FLAGS_BYTES = 1024;  // u32 flag[3 phases][2 buffers][KX_MAX_RA
 
 struct XCaps { uint32_t rows, blob, join; };  // per-rank slab rows / name bytes, keys of one sharded join
 
-struct SlabHeader {  // 64 bytes
-    uint32_t n_rows, blob_bytes, status, nkeys;
-    uint32_t pad[12];
-};
-struct SlabRow {  // 32 bytes: one winner (vendor,device) row of the shard
-    uint32_t key, name_len;
-    unsigned long long line, anchor;
-    uint32_t name_off, pad;
-};
-
 struct XLayout {
     size_t o_a[2], o_slab[2], slab_stride, o_res[2], total;
 };
@@ -152,40 +142,37 @@ __global__ void wait_flags_kernel(const WaitSpec W) { wait_flags_lane(W, (int)th
 
 struct XbParams {
     Targets tg;
-    size_t o_slab;  // my slab inside a region
+    int self;         // index of my own region in tg (its slab already holds the rows: nothing to copy), -1: none
+    const uint8_t *own_slab;
+    size_t o_slab;    // my slab inside a region
     uint32_t rows_cap, blob_cap;
     size_t o_flag;
     int raise_flags;
     uint32_t epoch;
     const uint32_t *counters;
-    const uint32_t *row_key, *row_name_off, *row_name_len;
-    const unsigned long long *row_line, *row_anchor;
-    const uint8_t *blob;
     uint32_t *done;
 };
 
-// Phase B: winner rows + their names, straight from the local table into this rank's slab in every
-// rank's region (32-byte row stores, 16-byte name stores over NVLink); the last CTA writes the header
+// Phase B: the winner rows and their names sit in this rank's own slab (the finalize wrote them
+// there); blockIdx.y picks the peer, the CTAs of that row stream rows + names into the peer's copy of
+// the slab with 16-byte stores over NVLink.  The CTA that finishes last writes the header everywhere
 // and raises the flags.
 __global__ void __launch_bounds__(256) xb_push_kernel(const XbParams P) {
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     const uint32_t n_sel = P.counters[KX_C_NSEL], blob_used = P.counters[KX_C_BLOB_CURSOR];
     uint32_t st = 0;
-    if (P.counters[KX_C_BLOB_OVERFLOW]) st |= XS_GROW_BLOB;
-    if (n_sel > P.rows_cap || blob_used > P.blob_cap) st |= XS_SLAB_OVERFLOW;
-    if (!st) {
-        for (size_t i = tid; i < n_sel; i += nth) {
-            SlabRow r;
-            r.key = P.row_key[i]; r.name_len = P.row_name_len[i]; r.line = P.row_line[i]; r.anchor = P.row_anchor[i];
-            r.name_off = P.row_name_off[i]; r.pad = 0;
-            for (int q = 0; q < P.tg.n; q++) reinterpret_cast<SlabRow *>(P.tg.region[q] + P.o_slab + slab_rows_off())[i] = r;
-        }
-        const size_t n16 = ((size_t)blob_used + 15) / 16;  // the blob lives in a 256-byte aligned arena with 16 bytes of slack
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(P.blob);
-        for (size_t i = tid; i < n16; i += nth) {
-            const uint4 x = s4[i];
-            for (int q = 0; q < P.tg.n; q++) reinterpret_cast<uint4 *>(P.tg.region[q] + P.o_slab + slab_blob_off(P.rows_cap))[i] = x;
-        }
+    if (P.counters[KX_C_BLOB_OVERFLOW] || n_sel > P.rows_cap || blob_used > P.blob_cap) st |= XS_SLAB_OVERFLOW;
+    const int q = (int)blockIdx.y;
+    if (!st && q != P.self) {
+        const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+        uint8_t *dst = P.tg.region[q] + P.o_slab;
+        const size_t r16 = (size_t)n_sel * (sizeof(SlabRow) / 16);
+        const uint4 *s_rows = reinterpret_cast<const uint4 *>(P.own_slab + slab_rows_off());
+        uint4 *d_rows = reinterpret_cast<uint4 *>(dst + slab_rows_off());
+        for (size_t i = tid; i < r16; i += nth) d_rows[i] = s_rows[i];
+        const size_t b16 = ((size_t)blob_used + 15) / 16;
+        const uint4 *s_blob = reinterpret_cast<const uint4 *>(P.own_slab + slab_blob_off(P.rows_cap));
+        uint4 *d_blob = reinterpret_cast<uint4 *>(dst + slab_blob_off(P.rows_cap));
+        for (size_t i = tid; i < b16; i += nth) d_blob[i] = s_blob[i];
     }
     // one system fence per CTA: the barrier makes the CTA's pushes visible to thread 0, whose
     // (cumulative) fence orders them in front of the counter and, in the last CTA, of the flags
@@ -193,7 +180,7 @@ __global__ void __launch_bounds__(256) xb_push_kernel(const XbParams P) {
     if (threadIdx.x == 0) {
         __threadfence_system();
         const uint32_t prev = atomicAdd(P.done, 1u);
-        if (prev == gridDim.x - 1u) {
+        if (prev == gridDim.x * gridDim.y - 1u) {
             *P.done = 0u;
             __threadfence_system();
             SlabHeader h;
@@ -202,10 +189,10 @@ __global__ void __launch_bounds__(256) xb_push_kernel(const XbParams P) {
             h.blob_bytes = st ? 0u : blob_used;
             h.status = st;
             h.nkeys = P.counters[KX_C_NKEYS];
-            for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<SlabHeader *>(P.tg.region[q] + P.o_slab) = h;
+            for (int k = 0; k < P.tg.n; k++) *reinterpret_cast<SlabHeader *>(P.tg.region[k] + P.o_slab) = h;
             __threadfence_system();
             if (P.raise_flags)
-                for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[q] + P.o_flag) = P.epoch;
+                for (int k = 0; k < P.tg.n; k++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[k] + P.o_flag) = P.epoch;
             __threadfence_system();
         }
     }
@@ -301,18 +288,35 @@ struct JoinParams {
     uint32_t *done;
 };
 
-// Phase C: probe this rank's key slice; every result goes into every rank's result buffer
-// (4-byte stores into peer memory, coalesced per warp) -- probe and all-gather of hits in one kernel.
+// Phase C: probe this rank's key slice; a CTA stages its 1024 hits in shared memory and warp w
+// streams the block into the result buffer of rank w, w + 8, ... (512 contiguous bytes per store
+// instruction over NVLink) -- probe and all-gather of hits in one kernel.  key_offset is a multiple
+// of 4 (16-byte alignment of every block) or the scalar tail path is used.
+constexpr int JOIN_PER_CTA = 1024;
 __global__ void __launch_bounds__(256) join_gather_kernel(const JoinParams P) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < P.n; i += stride) {
-        const int32_t row = kxparse::table_probe(P.slots, P.cap, P.shift, P.keys[i]);
-        for (int q = 0; q < P.tg.n; q++) reinterpret_cast<int32_t *>(P.tg.region[q] + P.o_res)[P.key_offset + i] = row;
+    __shared__ __align__(16) int32_t res[JOIN_PER_CTA];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    for (size_t b0 = (size_t)blockIdx.x * JOIN_PER_CTA; b0 < P.n; b0 += (size_t)gridDim.x * JOIN_PER_CTA) {
+        const uint32_t cnt = P.n - b0 < (size_t)JOIN_PER_CTA ? (uint32_t)(P.n - b0) : (uint32_t)JOIN_PER_CTA;
+#pragma unroll
+        for (int k = 0; k < JOIN_PER_CTA / 256; k++) {
+            const uint32_t j = tid + 256u * k;
+            if (j < cnt) res[j] = kxparse::table_probe(P.slots, P.cap, P.shift, P.keys[b0 + j]);
+        }
+        __syncthreads();
+        const size_t o = P.key_offset + b0;
+        for (int q = (int)w; q < P.tg.n; q += 8) {
+            int32_t *dst = reinterpret_cast<int32_t *>(P.tg.region[q] + P.o_res) + o;
+            if (cnt == (uint32_t)JOIN_PER_CTA && (o & 3u) == 0u) {
+#pragma unroll
+                for (int k = 0; k < JOIN_PER_CTA / 128; k++)
+                    reinterpret_cast<uint4 *>(dst)[lane + 32 * k] = reinterpret_cast<const uint4 *>(res)[lane + 32 * k];
+            } else {
+                for (uint32_t j = lane; j < cnt; j += 32u) dst[j] = res[j];
+            }
+        }
+        __syncthreads();
     }
-    // one system fence per CTA: the barrier makes the CTA's pushes visible to thread 0, whose
-    // (cumulative) fence orders them in front of the counter and, in the last CTA, of the flags
-    __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
         const uint32_t prev = atomicAdd(P.done, 1u);
@@ -589,17 +593,21 @@ static void shard_phase2(ShardOp &op) {
     }
     g_trace.mark(3, ctx->stream);
     const unsigned long long *a = reinterpret_cast<const unsigned long long *>(mine + L.o_a[op.b]);
-    op.rc = kx_launch_finalize(ctx, t, op.a.d_text, op.a.n, op.a.base, a, a + A_TRUNC, &ws);
+    // winners (judged against the all-reduced minima) are sanitised straight into my own slab
+    const uint32_t rows_cap = op.nccl ? x->scaps.rows : x->caps.rows, blob_cap = op.nccl ? x->scaps.blob : x->caps.blob;
+    uint8_t *own_slab = op.nccl ? x->send_slab : mine + L.o_slab[op.b] + (size_t)x->rank * L.slab_stride;
+    KxSlabOut so{own_slab + slab_rows_off(), rows_cap, own_slab + slab_blob_off(rows_cap), blob_cap};
+    op.rc = kx_launch_finalize(ctx, t, op.a.d_text, op.a.n, op.a.base, a, a + A_TRUNC, &ws, &so);
     if (op.rc != KXPU_OK) return;
     g_trace.mark(4, ctx->stream);
     XbParams P;
     memset(&P, 0, sizeof P);
-    if (op.nccl) { P.tg.n = 1; P.tg.region[0] = x->send_slab; P.o_slab = 0; P.rows_cap = x->scaps.rows; P.blob_cap = x->scaps.blob; }
-    else { P.tg = targets(op); P.o_slab = L.o_slab[op.b] + (size_t)x->rank * L.slab_stride; P.rows_cap = x->caps.rows; P.blob_cap = x->caps.blob; }
+    if (op.nccl) { P.tg.n = 1; P.tg.region[0] = x->send_slab; P.o_slab = 0; P.self = 0; }
+    else { P.tg = targets(op); P.o_slab = L.o_slab[op.b] + (size_t)x->rank * L.slab_stride; P.self = x->rank; }
+    P.own_slab = own_slab; P.rows_cap = rows_cap; P.blob_cap = blob_cap;
     P.o_flag = flag_off(1, op.b, x->rank); P.raise_flags = op.nccl ? 0 : 1; P.epoch = op.epoch;
-    P.counters = t->dev.counters; P.row_key = t->row_key; P.row_name_off = t->row_name_off; P.row_name_len = t->row_name_len;
-    P.row_line = t->row_line; P.row_anchor = t->row_anchor; P.blob = t->blob; P.done = x->scratch + 1;
-    xb_push_kernel<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(P);
+    P.counters = t->dev.counters; P.done = x->scratch + 1;
+    xb_push_kernel<<<dim3(op.nccl ? 1u : 64u, (unsigned)P.tg.n), 256, 0, ctx->stream>>>(P);
     KX_LAUNCHED(ctx);
     g_trace.mark(5, ctx->stream);
 }
@@ -650,8 +658,8 @@ static void shard_phase3(ShardOp &op) {
     J.keys = op.a.d_keys; J.n = op.a.nq; J.key_offset = op.a.key_offset; J.slots = t->dev.slots; J.cap = t->cap; J.shift = t->shift;
     J.tg = targets(op); J.o_res = L.o_res[op.b]; J.o_flag = flag_off(2, op.b, x->rank); J.raise_flags = 1; J.epoch = op.epoch;
     J.done = x->scratch + 2;
-    size_t blocks = std::max<size_t>((op.a.nq + 255) / 256, 1);
-    blocks = std::min<size_t>(blocks, (size_t)ctx->sm_count * 16);
+    size_t blocks = std::max<size_t>((op.a.nq + JOIN_PER_CTA - 1) / JOIN_PER_CTA, 1);
+    blocks = std::min<size_t>(blocks, (size_t)ctx->sm_count * 8);
     join_gather_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(J);
     KX_LAUNCHED(ctx);
     g_trace.mark(8, ctx->stream);

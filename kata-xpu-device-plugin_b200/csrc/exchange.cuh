@@ -18,6 +18,16 @@ constexpr int A_TRUNC = 65536;    // phase-A block: u64 [65536] vendor_first | t
 constexpr int A_STATUS0 = 65537;  // status bit k is set iff word A_STATUS0 + k == 0 (so that min all-reduces it)
 constexpr int A_WORDS = 65536 + 8;
 
+struct SlabHeader {  // 64 bytes
+    uint32_t n_rows, blob_bytes, status, nkeys;
+    uint32_t pad[12];
+};
+struct SlabRow {  // 32 bytes: one winner (vendor,device) row of the shard
+    uint32_t key, name_len;
+    unsigned long long line, anchor;
+    uint32_t name_off, pad;
+};
+
 struct Targets {  // where a push goes: every rank's region (peer memory) or this rank's staging region (NCCL)
     uint8_t *region[KX_MAX_RANKS];
     int n;

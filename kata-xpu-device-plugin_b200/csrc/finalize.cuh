@@ -96,8 +96,10 @@ __device__ __forceinline__ uint32_t sanitise_byte(const uint8_t *buf, uint32_t i
     return 0u;
 }
 
-constexpr int NAME_BUF = 1024;  // fast path: rest-of-line fits the per-warp staging buffer
-constexpr int FIN_WARPS = 8;
+constexpr int SF_WARPS = 8;
+constexpr int SF_WIN = 128;  // bytes of a line a row group looks at (eight lanes x one aligned 16-byte load)
+constexpr int SF_BATCH = 8;  // table slots per warp and step: ~30 % are valid, so a step is usually ONE round of four rows --
+                             // small batches keep ~8 000 warps in flight, each with a single chain of dependent loads
 
 struct FinalizeParams {
     const uint8_t *text;  // shard text (local)
@@ -112,150 +114,281 @@ struct FinalizeParams {
     unsigned long long *row_anchor;
     uint32_t *row_name_off;
     uint32_t *row_name_len;
-    uint32_t *sel;  // [cap+1] valid slots (stage 1 -> stage 2)
     uint8_t *blob;
     uint32_t blob_cap;
-    kxx::WaitSpec wait;  // sharded load: the all-reduced minima are complete when these flags are up
+    kxx::WaitSpec wait;       // sharded load: the all-reduced minima are complete when these flags are up
+    kxx::SlabRow *slab_rows;  // sharded load: rows go here (this rank's slab, 32-byte records) instead of the row arrays
+    uint32_t slab_rows_cap;
 };
 
-// Stage 1, one thread per table slot: validity; valid slots are compacted into F.sel.
-// KX_C_NEED_TRUNC: 0 = cut-off never computed, 1 = computed (host ran trunc_kernel), 2 = asked
-// for.  When the parse raised the long-line hint and the cut-off is not there yet, every block
-// leaves (the test does not depend on what block 0 writes) and the host finalizes again.
-__global__ void __launch_bounds__(256) finalize_select_kernel(const FinalizeParams F) {
-    kxx::wait_flags_cta(F.wait);
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (F.tab.counters[KX_C_LONGLINE_HINT] != 0u && F.tab.counters[KX_C_NEED_TRUNC] != 1u) {
-        if (slot == 0) F.tab.counters[KX_C_NEED_TRUNC] = 2u;
-        return;
-    }
-    bool valid = false;
-    if (slot <= F.tab.cap) {
-        const uint4 head = *reinterpret_cast<const uint4 *>(&F.tab.slots[slot]);
-        const unsigned long long line = ((unsigned long long)head.w << 32) | head.z;
-        const uint32_t key = slot == F.tab.cap ? KX_EMPTY_KEY : head.x;
-        valid = line != KX_NO_OFF && !(slot < F.tab.cap && key == KX_EMPTY_KEY);
-        if (valid) valid = F.tab.slots[slot].min_anchor == F.vendor_first[key >> 16] && line < *F.trunc;
-    }
-    const uint32_t vm = __ballot_sync(0xffffffffu, valid);
-    if (vm) {
-        uint32_t base = 0;
-        if ((threadIdx.x & 31u) == 0) base = atomicAdd(&F.tab.counters[KX_C_NSEL], (uint32_t)__popc(vm));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (valid) F.sel[base + (uint32_t)__popc(vm & ((1u << (threadIdx.x & 31u)) - 1u))] = slot;
+__device__ __forceinline__ void finalize_store_row(const FinalizeParams &F, uint32_t row, uint32_t slot, uint32_t key, unsigned long long line,
+                                                   unsigned long long anchor, uint32_t name_off, uint32_t name_len) {
+    F.tab.slots[slot].row = (int32_t)row;
+    if (F.slab_rows) {
+        if (row < F.slab_rows_cap) {
+            kxx::SlabRow r;
+            r.key = key; r.name_len = name_len; r.line = line; r.anchor = anchor; r.name_off = name_off; r.pad = 0u;
+            F.slab_rows[row] = r;
+        }
+    } else {
+        F.row_key[row] = key; F.row_line[row] = line; F.row_anchor[row] = anchor;
+        F.row_name_off[row] = name_off; F.row_name_len[row] = name_len;
     }
 }
 
-// Stage 2, one warp per selected slot (row handle = index in F.sel): sanitised name into the
-// blob.  Persistent grid: a CTA takes groups of 8 selected slots until the (device-side) count is
-// used up, so a load that selects nothing costs one wave of CTAs that read the count and leave.
-// Blob space is claimed once per group (8 names) to keep the cursor atomic cheap.
-__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(const FinalizeParams F) {
-    __shared__ uint8_t s_buf[FIN_WARPS][NAME_BUF + 32];
-    __shared__ uint32_t s_len[FIN_WARPS];
-    __shared__ uint32_t s_base;
-    const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5;
-    const uint32_t nsel = F.tab.counters[KX_C_NSEL];
-    uint8_t *buf = s_buf[wl];
-    for (uint32_t g0 = blockIdx.x * FIN_WARPS; g0 < nsel; g0 += gridDim.x * FIN_WARPS) {
-        const uint32_t si = g0 + wl;
-        const bool active = si < nsel;
-        uint32_t slot = 0, key = 0, len = 0, start = 0, end = 0, out_len = 0;
-        unsigned long long line = 0, anchor = 0, rs = 0;
-        bool fast = false;
-        if (active) {
-            slot = F.sel[si];
-            line = F.tab.slots[slot].min_line;
-            key = slot == F.tab.cap ? KX_EMPTY_KEY : F.tab.slots[slot].key;
-            anchor = F.tab.slots[slot].min_anchor;
-            rs = line - F.base + 5ull;  // rest of the line after "\t" + 4 hex digits
-            bool found = false;
-            for (uint32_t o = 0; o < (uint32_t)NAME_BUF + 32u && !found; o += 128u) {
-                // 128 bytes per step: most names end inside the first one
-                uint32_t nlm[4];
+// Validity + names in ONE kernel.  A warp takes SF_BATCH consecutive table slots; the valid ones
+// (min_anchor == first anchor of the vendor, line in front of the ErrTooLong cut-off) are worked off
+// four at a time, eight lanes per row: one aligned 16-byte load per lane brings 128 bytes of the
+// line, the lanes find the newline, trim (strings.TrimSpace), sanitise their 16 bytes each
+// (device_plugin.go:241-251) and compact the result into a shared-memory staging row.  Per batch the
+// warp claims row handles and blob space with one atomic each and copies the names out.  Lines whose
+// rest does not end inside the window (never in device lines of pci.ids' NVIDIA block) take a serial
+// path.  KX_C_NEED_TRUNC: 0 = cut-off never computed, 1 = computed (trunc_kernel), 2 = asked for:
+// when the parse raised the long-line hint and the cut-off is not there yet, every block leaves
+// (the test does not depend on what block 0 writes) and the host finalizes again.
+__global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const FinalizeParams F) {
+    __shared__ __align__(16) uint8_t s_raw[SF_WARPS][4][SF_WIN + 16];
+    __shared__ uint8_t s_name[SF_WARPS][SF_BATCH][SF_WIN];
+    __shared__ uint32_t s_cnt[SF_WARPS], s_bytes[SF_WARPS], s_row0, s_blob0;
+    kxx::wait_flags_cta(F.wait);
+    if (F.tab.counters[KX_C_LONGLINE_HINT] != 0u && F.tab.counters[KX_C_NEED_TRUNC] != 1u) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) F.tab.counters[KX_C_NEED_TRUNC] = 2u;
+        return;
+    }
+    const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5, sub = lane & 7u, grp = lane >> 3;
+    const uint32_t nslots = F.tab.cap + 1u;
+    const unsigned long long trunc = *F.trunc;
+    // the CTA's warps step together: row handles and blob space are claimed once per CTA and step
+    // (same-address atomics run at ~1 per ns: one pair per warp and step was the whole kernel time)
+    for (uint32_t c0 = blockIdx.x * SF_WARPS * (uint32_t)SF_BATCH; c0 < nslots; c0 += gridDim.x * SF_WARPS * (uint32_t)SF_BATCH) {
+        const uint32_t s0 = c0 + wl * (uint32_t)SF_BATCH;
+        const uint32_t slot = s0 + lane;
+        bool valid = false;
+        uint32_t key = 0;
+        unsigned long long line = 0, anchor = 0;
+        if (lane < (uint32_t)SF_BATCH && slot < nslots) {
+            const uint4 head = *reinterpret_cast<const uint4 *>(&F.tab.slots[slot]);
+            line = ((unsigned long long)head.w << 32) | head.z;
+            key = slot == F.tab.cap ? KX_EMPTY_KEY : head.x;
+            valid = line != KX_NO_OFF && !(slot < F.tab.cap && key == KX_EMPTY_KEY);
+            if (valid) {
+                anchor = F.tab.slots[slot].min_anchor;
+                valid = anchor == F.vendor_first[key >> 16] && line < trunc;
+            }
+        }
+        const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+        const uint32_t nvalid = (uint32_t)__popc(vm);
+        const uint32_t myrank = (uint32_t)__popc(vm & ((1u << lane) - 1u));  // row of this lane's slot inside the batch
+        uint32_t my_len = 0;    // lane r (< nvalid): sanitised length of batch row r
+        uint32_t slow_m = 0;    // batch rows that need the serial path
+        for (uint32_t r0 = 0; r0 < nvalid; r0 += 4u) {
+            const uint32_t r = r0 + grp;  // batch row of my group
+            const bool act = r < nvalid;
+            // the lane that owns batch row r0 + g (its myrank-th valid slot), for the four groups
+            uint32_t src = 0;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const unsigned long long pos = rs + o + 32u * k + lane;
-                    const uint32_t c = pos < F.n ? F.text[pos] : 0x0au;  // EOF terminates the last line
-                    if (o + 32u * k < (uint32_t)NAME_BUF + 32u) buf[o + 32u * k + lane] = (uint8_t)c;
-                    nlm[k] = __ballot_sync(0xffffffffu, c == 0x0au);
+            for (uint32_t g = 0; g < 4u; g++) {
+                const uint32_t own = __ballot_sync(0xffffffffu, valid && myrank == r0 + g);
+                if (grp == g && own) src = (uint32_t)__ffs((int)own) - 1u;
+            }
+            const unsigned long long rline = __shfl_sync(0xffffffffu, line, src);
+            const uint32_t gmask = 0xffu << (8u * grp);  // my row group: its eight lanes take every branch below together
+            uint32_t total = 0, start = 0, end = 0;
+            bool slow = false;
+            const uint8_t *buf = s_raw[wl][grp];
+            if (act) {
+                const unsigned long long rs = rline - F.base + 5ull;  // rest of the line after "\t" + 4 hex digits
+                const unsigned long long a0 = rs & ~15ull;
+                const uint32_t lead = (uint32_t)(rs - a0);
+                const unsigned long long p0 = a0 + 16ull * sub;
+                uint4 q;
+                if (p0 + 16ull <= F.n) {
+                    q = *reinterpret_cast<const uint4 *>(F.text + p0);
+                } else {
+                    uint8_t tmp[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) tmp[k] = p0 + k < F.n ? F.text[p0 + k] : (uint8_t)0x0a;  // EOF terminates the last line
+                    q = *reinterpret_cast<uint4 *>(tmp);
                 }
+                uint8_t *raw = s_raw[wl][grp];
+                *reinterpret_cast<uint4 *>(raw + 16u * sub) = q;
+                // first newline at or behind `lead`: SWAR byte-equality mask of my 16 bytes (bit k = byte k is '\n')
+                uint32_t nlm = 0;
+                {
+                    const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (!found && nlm[k]) { len = o + 32u * k + (uint32_t)__ffs((int)nlm[k]) - 1u; found = true; }
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t y = w4[k] ^ 0x0a0a0a0au;
+                        const uint32_t z = ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y | 0x7f7f7f7fu);  // 0x80 where the byte is zero
+                        nlm |= (((z >> 7) * 0x00204081u) >> 21 & 0xfu) << (4 * k);      // gather the four flags
+                    }
+                    if (sub == 0u) nlm &= 0xffffu << lead;
+                }
+                const uint32_t pos = nlm ? (uint32_t)__ffs((int)nlm) - 1u : 16u;
+                uint32_t first = pos < 16u ? 16u * sub + pos : (uint32_t)SF_WIN;
+#pragma unroll
+                for (int d = 4; d > 0; d >>= 1) {
+                    const uint32_t o = __shfl_xor_sync(gmask, first, d, 8);
+                    first = o < first ? o : first;
+                }
+                __syncwarp(gmask);
+                if (first >= (uint32_t)SF_WIN) {
+                    slow = true;
+                } else {
+                    buf = raw + lead;
+                    uint32_t len = first - lead;
+                    if (len > 0 && buf[len - 1] == 0x0du) len--;  // bufio.ScanLines drops one trailing CR
+                    if (sub == 0) trim_space(buf, len, start, end);
+                    start = __shfl_sync(gmask, start, 0, 8);
+                    end = __shfl_sync(gmask, end, 0, 8);
+                }
+            }
+            // sanitise (device_plugin.go:241-251), one byte per lane and step, eight bytes per row and
+            // step, all four rows of the warp in lock step; the surviving bytes are compacted with a
+            // ballot into the row's staging line.  Branch free: every lane runs every step.
+            {
+                const uint32_t span = __reduce_max_sync(0xffffffffu, end - start);
+                uint8_t *dst = s_name[wl][act ? r : 0u];
+                for (uint32_t o = 0; o < span; o += 8u) {
+                    const uint32_t i = start + o + sub;
+                    const bool in = i < end;
+                    const uint32_t c = in ? buf[i] : 0x41u;
+                    const uint32_t prev = (in && i > start) ? buf[i - 1] : 0x41u;  // a space run never starts in front of the trimmed range
+                    const uint32_t nx = (in && i + 1u < end) ? buf[i + 1] : 0u;
+                    const bool sp = c <= 32u && ((0x100003600ull >> c) & 1ull);      // RE2 \s: [\t\n\f\r ]
+                    const bool psp = prev <= 32u && ((0x100003600ull >> prev) & 1ull);
+                    uint32_t ch = 0;
+                    ch = (c - 0x61u < 26u) ? c - 32u : ch;                          // ToUpper
+                    ch = (c - 0x41u < 26u || c - 0x30u < 10u || c == 0x5fu) ? c : ch;
+                    ch = (c == 0x2fu || c == 0x2eu) ? 0x5fu : ch;                   // '/' '.' -> '_'
+                    ch = sp ? (psp ? 0u : 0x5fu) : ch;                              // \s+ -> one '_'
+                    ch = (c == 0xC4u && nx == 0xB1u) ? 0x49u : ch;                   // U+0131 upper-cases to ASCII I
+                    ch = (c == 0xC5u && nx == 0xBFu) ? 0x53u : ch;                   // U+017F upper-cases to ASCII S
+                    ch = in ? ch : 0u;
+                    const uint32_t gm = (__ballot_sync(0xffffffffu, ch != 0u) >> (8u * grp)) & 0xffu;
+                    if (ch) dst[total + (uint32_t)__popc(gm & ((1u << sub) - 1u))] = (uint8_t)ch;
+                    total += (uint32_t)__popc(gm);
+                }
+            }
+            // lane r0 + g learns the length of batch row r0 + g (from group g)
+            const uint32_t gtot = __shfl_sync(0xffffffffu, total, (lane & 3u) * 8u);
+            const uint32_t gslow = __ballot_sync(0xffffffffu, slow && sub == 0u);
+            if (lane >= r0 && lane < r0 + 4u && lane < nvalid) my_len = gtot;
+            for (uint32_t g = 0; g < 4u; g++)
+                if ((gslow >> (8u * g)) & 1u) slow_m |= 1u << (r0 + g);
+        }
+        __syncwarp();
+        // one claim of row handles and of blob space per batch
+        uint32_t len_r = (lane < nvalid && !((slow_m >> lane) & 1u)) ? my_len : 0u;
+        uint32_t incl = len_r;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += y;
+        }
+        const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) { s_cnt[wl] = nvalid; s_bytes[wl] = wtot; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t rows = 0, bytes = 0;
+#pragma unroll
+            for (int k = 0; k < SF_WARPS; k++) { rows += s_cnt[k]; bytes += s_bytes[k]; }
+            s_row0 = rows ? atomicAdd(&F.tab.counters[KX_C_NSEL], rows) : 0u;
+            uint32_t b0 = bytes ? atomicAdd(&F.tab.counters[KX_C_BLOB_CURSOR], bytes) : 0u;
+            if (b0 + bytes > F.blob_cap) { F.tab.counters[KX_C_BLOB_OVERFLOW] = 1u; b0 = 0xFFFFFFFFu; }
+            s_blob0 = b0;
+        }
+        __syncthreads();
+        uint32_t row0 = s_row0, blob0 = s_blob0;
+        for (uint32_t k = 0; k < wl; k++) { row0 += s_cnt[k]; if (blob0 != 0xFFFFFFFFu) blob0 += s_bytes[k]; }
+        const bool room = blob0 != 0xFFFFFFFFu;
+        const uint32_t off_r = room ? blob0 + incl - len_r : 0u;
+        // names out: one row at a time, 32 bytes per step
+        for (uint32_t r = 0; r < nvalid; r++) {
+            const uint32_t L = __shfl_sync(0xffffffffu, len_r, r), O = __shfl_sync(0xffffffffu, off_r, r);
+            if (room)
+                for (uint32_t j = lane; j < L; j += 32u) F.blob[O + j] = s_name[wl][r][j];
+        }
+        // row records: the lane that owns the slot writes its row (batch row = myrank)
+        const uint32_t my_row_len = __shfl_sync(0xffffffffu, len_r, valid ? myrank : 0u);
+        const uint32_t my_row_off = __shfl_sync(0xffffffffu, off_r, valid ? myrank : 0u);
+        const bool my_slow = valid && ((slow_m >> myrank) & 1u);
+        if (valid && !my_slow) finalize_store_row(F, row0 + myrank, slot, key, line, anchor, room ? my_row_off : 0u, room ? my_row_len : 0u);
+        // long lines (the rest does not end inside the 128-byte window; 19 device lines of pci.ids):
+        // the whole warp takes them one at a time -- the line is staged into the (now free) name staging
+        // area 32 bytes per step, then sanitised one byte per lane with ballot compaction
+        __syncwarp();
+        for (uint32_t sm = slow_m; sm; sm &= sm - 1u) {
+            const uint32_t r = (uint32_t)__ffs((int)sm) - 1u;
+            const uint32_t own = __ballot_sync(0xffffffffu, valid && myrank == r);
+            const uint32_t ol = (uint32_t)__ffs((int)own) - 1u;
+            const unsigned long long l_line = __shfl_sync(0xffffffffu, line, ol), l_anchor = __shfl_sync(0xffffffffu, anchor, ol);
+            const uint32_t l_key = __shfl_sync(0xffffffffu, key, ol), l_slot = __shfl_sync(0xffffffffu, slot, ol);
+            const unsigned long long rs = l_line - F.base + 5ull;
+            uint8_t *buf = &s_name[wl][0][0];
+            constexpr uint32_t LONG_MAX_LEN = (uint32_t)(SF_BATCH * SF_WIN) - 32u;
+            uint32_t len = 0;
+            bool found = false;
+            for (uint32_t o = 0; o < LONG_MAX_LEN + 32u && !found; o += 32u) {
+                const unsigned long long pos = rs + o + lane;
+                const uint32_t c = pos < F.n ? F.text[pos] : 0x0au;  // EOF terminates the last line
+                buf[o + lane] = (uint8_t)c;
+                const uint32_t nlm = __ballot_sync(0xffffffffu, c == 0x0au);
+                if (nlm) { len = o + (uint32_t)__ffs((int)nlm) - 1u; found = true; }
             }
             __syncwarp();
-            fast = found && len <= (uint32_t)NAME_BUF;
-            if (fast) {
+            uint32_t start = 0, end = 0, out_len = 0, at = 0;
+            bool ok = true;
+            if (found) {
                 if (len > 0 && buf[len - 1] == 0x0du) len--;  // bufio.ScanLines drops one trailing CR
                 if (lane == 0) trim_space(buf, len, start, end);
                 start = __shfl_sync(0xffffffffu, start, 0);
                 end = __shfl_sync(0xffffffffu, end, 0);
                 for (uint32_t o = start; o < end; o += 32u) {
-                    uint32_t i = o + lane;
-                    uint32_t ch = i < end ? sanitise_byte(buf, i, start, end) : 0u;
+                    const uint32_t i = o + lane;
+                    const uint32_t ch = i < end ? sanitise_byte(buf, i, start, end) : 0u;
                     out_len += (uint32_t)__popc(__ballot_sync(0xffffffffu, ch != 0u));
                 }
-            } else {
-                // slow path: a name longer than the staging buffer (never in pci.ids): lane 0, serial,
-                // straight from global memory.
                 if (lane == 0) {
-                    const uint8_t *g = F.text + rs;
-                    unsigned long long avail = F.n - rs, l = 0;
-                    while (l < avail && g[l] != 0x0au) l++;
-                    len = (uint32_t)l;
-                    if (len > 0 && g[len - 1] == 0x0du) len--;
-                    trim_space(g, len, start, end);
-                    for (uint32_t i = start; i < end; i++) out_len += sanitise_byte(g, i, start, end) != 0u;
+                    at = out_len ? atomicAdd(&F.tab.counters[KX_C_BLOB_CURSOR], out_len) : 0u;
+                    if (at + out_len > F.blob_cap) { F.tab.counters[KX_C_BLOB_OVERFLOW] = 1u; at = 0xFFFFFFFFu; }
                 }
-                out_len = __shfl_sync(0xffffffffu, out_len, 0);
-                start = __shfl_sync(0xffffffffu, start, 0);
-                end = __shfl_sync(0xffffffffu, end, 0);
-            }
-        }
-        if (lane == 0) s_len[wl] = out_len;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t tot = 0;
-            for (int k = 0; k < FIN_WARPS; k++) tot += s_len[k];
-            uint32_t base = tot ? atomicAdd(&F.tab.counters[KX_C_BLOB_CURSOR], tot) : 0u;
-            if (base + tot > F.blob_cap) { F.tab.counters[KX_C_BLOB_OVERFLOW] = 1u; base = 0xFFFFFFFFu; }
-            s_base = base;
-        }
-        __syncthreads();
-        if (active) {
-            uint32_t out_off = s_base;
-            const bool room = out_off != 0xFFFFFFFFu;
-            for (uint32_t k = 0; k < wl; k++) out_off += s_len[k];
-            if (room) {
-                if (fast) {
-                    uint32_t wr = out_off;
+                at = __shfl_sync(0xffffffffu, at, 0);
+                ok = at != 0xFFFFFFFFu;
+                if (ok) {
+                    uint32_t wr = at;
                     for (uint32_t o = start; o < end; o += 32u) {
-                        uint32_t i = o + lane;
-                        uint32_t ch = i < end ? sanitise_byte(buf, i, start, end) : 0u;
-                        uint32_t bm = __ballot_sync(0xffffffffu, ch != 0u);
+                        const uint32_t i = o + lane;
+                        const uint32_t ch = i < end ? sanitise_byte(buf, i, start, end) : 0u;
+                        const uint32_t bm = __ballot_sync(0xffffffffu, ch != 0u);
                         if (ch) F.blob[wr + (uint32_t)__popc(bm & ((1u << lane) - 1u))] = (uint8_t)ch;
                         wr += (uint32_t)__popc(bm);
                     }
-                } else if (lane == 0) {
-                    const uint8_t *g = F.text + rs;
-                    uint32_t wr = out_off;
+                }
+            } else if (lane == 0) {
+                // longer than the staging area (never in pci.ids): lane 0, serial, straight from global memory
+                const uint8_t *g = F.text + rs;
+                const unsigned long long avail = F.n - rs;
+                unsigned long long l = 0;
+                while (l < avail && g[l] != 0x0au) l++;
+                len = (uint32_t)l;
+                if (len > 0 && g[len - 1] == 0x0du) len--;
+                trim_space(g, len, start, end);
+                for (uint32_t i = start; i < end; i++) out_len += sanitise_byte(g, i, start, end) != 0u;
+                at = out_len ? atomicAdd(&F.tab.counters[KX_C_BLOB_CURSOR], out_len) : 0u;
+                if (at + out_len > F.blob_cap) { F.tab.counters[KX_C_BLOB_OVERFLOW] = 1u; ok = false; }
+                if (ok) {
+                    uint32_t wr = at;
                     for (uint32_t i = start; i < end; i++) {
-                        uint32_t ch = sanitise_byte(g, i, start, end);
+                        const uint32_t ch = sanitise_byte(g, i, start, end);
                         if (ch) F.blob[wr++] = (uint8_t)ch;
                     }
                 }
             }
-            if (lane == 0) {
-                F.tab.slots[slot].row = (int32_t)si;
-                F.row_key[si] = key;
-                F.row_line[si] = line;
-                F.row_anchor[si] = anchor;
-                F.row_name_off[si] = room ? out_off : 0u;
-                F.row_name_len[si] = room ? out_len : 0u;
-            }
+            if (lane == 0) finalize_store_row(F, row0 + r, l_slot, l_key, l_line, l_anchor, ok ? at : 0u, ok ? out_len : 0u);
+            __syncwarp();
         }
-        __syncthreads();  // s_len / s_base / the staging buffers are reused by the next group
+        __syncthreads();  // the staging rows and the claim words are reused by the next step
     }
 }
 

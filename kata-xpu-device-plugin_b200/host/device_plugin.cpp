@@ -72,42 +72,88 @@ Plugin::~Plugin() {
     if (table_) kxpu_table_free(ctx_, table_);
 }
 
+// the Trim half of readIDFromFileFunc (:189): data[2:] with '\n' trimmed at both ends
+static std::string trimID(const std::string &raw) {
+    if (raw.size() < 2) return std::string();
+    size_t a = 2, b = raw.size();
+    while (a < b && raw[a] == '\n') a++;
+    while (b > a && raw[b - 1] == '\n') b--;
+    return raw.substr(a, b - a);
+}
+
+// an id file as the record carries it: the raw bytes when they fit the 8-byte field, else the
+// canonical spelling "0x" + id + "\n" of the same id (identical after the reference's data[2:] /
+// Trim); false when even that does not fit (the id itself is longer than 5 characters)
+static bool packID(const std::string &raw, uint8_t txt[8], uint8_t &len) {
+    if (raw.size() <= 8) {
+        memcpy(txt, raw.data(), raw.size());
+        len = (uint8_t)raw.size();
+        return true;
+    }
+    const std::string id = trimID(raw);
+    if (id.size() > 5 || id.find('\n') != std::string::npos) return false;
+    const std::string canon = "0x" + id + "\n";
+    memcpy(txt, canon.data(), canon.size());
+    len = (uint8_t)canon.size();
+    return true;
+}
+
 // The body of the walk callback for one non-directory entry (device_plugin.go:141-175, the reads
-// only): raw bytes of `vendor` / `device`, basenames of the `driver` / `iommu_group` links.
+// only, in the reference's order and as lazily as the reference: nothing is read behind a vendor
+// that is not 10de or a driver that is not vfio-pci): raw bytes of `vendor` / `device`, basenames
+// of the `driver` / `iommu_group` links.  An entry the record cannot carry (address longer than 15
+// bytes, group that is not a canonical decimal below 2^32-1, id longer than the field) is logged and
+// skipped like a read error -- and only if the reference would have accepted it; it never stops the walk.
 template <typename ReadID, typename ReadLnk>
 static Error leafRecord(const std::string &name, ReadID readID, ReadLnk readLnk, kxpu_devrec &r) {
     memset(&r, 0, sizeof r);
+    strncpy(r.bdf, name.c_str(), sizeof r.bdf - 1);
     std::string s;
-    bool vendor_ok = readID("vendor", s);
-    if (!vendor_ok) {
-        r.flags |= KXPU_REC_VENDOR_ERR;  // "Could not get vendor ID for device" -> skipped
-        strncpy(r.bdf, name.c_str(), sizeof r.bdf - 1);
+    if (!readID("vendor", s)) {
+        r.flags |= KXPU_REC_VENDOR_ERR;  // "Could not get vendor ID for device" -> skipped (:143-146)
         return Error();
     }
-    if (name.size() > sizeof r.bdf - 1) return fail("PCI address longer than 15 bytes: " + name);
-    memcpy(r.bdf, name.data(), name.size());
-    r.vendor_len = (uint8_t)std::min<size_t>(s.size(), 255);
-    memcpy(r.vendor_txt, s.data(), std::min<size_t>(s.size(), 8));
-    if (readLnk("driver", s)) {
-        memcpy(r.driver, s.data(), std::min<size_t>(s.size(), sizeof r.driver - 1));
-    } else {
-        r.flags |= KXPU_REC_DRIVER_ERR;
+    const bool nvidia = trimID(s) == "10de";  // :149
+    if (!packID(s, r.vendor_txt, r.vendor_len)) {  // an id of six or more characters is not 10de
+        memcpy(r.vendor_txt, s.data(), 8);
+        r.vendor_len = 8;
+        r.flags |= KXPU_REC_VENDOR_ERR;
     }
-    if (readLnk("iommu_group", s)) {
+    if (!nvidia) return Error();
+    if (!readLnk("driver", s)) {
+        r.flags |= KXPU_REC_DRIVER_ERR;  // :152-155
+        return Error();
+    }
+    memcpy(r.driver, s.data(), std::min<size_t>(s.size(), sizeof r.driver - 1));
+    if (s != "vfio-pci") return Error();  // :156
+    if (name.size() > sizeof r.bdf - 1) {
+        fprintf(stderr, "PCI address longer than 15 bytes, device skipped: %s\n", name.c_str());
+        r.flags |= KXPU_REC_IOMMU_ERR;
+        return Error();
+    }
+    if (readLnk("iommu_group", s)) {  // :157
         bool dec = !s.empty() && s.size() <= 10;
         unsigned long long v = 0;
         for (char c : s) { if (c < '0' || c > '9') dec = false; else v = v * 10 + (unsigned)(c - '0'); }
-        if (!dec || v >= 0xFFFFFFFFull || (s.size() > 1 && s[0] == '0'))
-            return fail("iommu_group of " + name + " is not a canonical decimal number: " + s);
+        if (!dec || v >= 0xFFFFFFFFull || (s.size() > 1 && s[0] == '0')) {
+            fprintf(stderr, "iommu_group of %s is not a canonical decimal number below 2^32-1, device skipped: %s\n", name.c_str(), s.c_str());
+            r.flags |= KXPU_REC_IOMMU_ERR;
+            return Error();
+        }
         r.iommu_group = (uint32_t)v;
     } else {
-        r.flags |= KXPU_REC_IOMMU_ERR;
+        r.flags |= KXPU_REC_IOMMU_ERR;  // :158-161
+        return Error();
     }
+    // :164 reads `device` only for the first member of a group; which record that is is decided on
+    // the GPU, so the file is read for every accepted candidate (a failure only matters for a first member)
     if (readID("device", s)) {
-        r.device_len = (uint8_t)std::min<size_t>(s.size(), 255);
-        memcpy(r.device_txt, s.data(), std::min<size_t>(s.size(), 8));
+        if (!packID(s, r.device_txt, r.device_len)) {
+            fprintf(stderr, "device id of %s is longer than the record field, device skipped\n", name.c_str());
+            r.flags |= KXPU_REC_DEVICE_ERR;
+        }
     } else {
-        r.flags |= KXPU_REC_DEVICE_ERR;
+        r.flags |= KXPU_REC_DEVICE_ERR;  // :165-168
     }
     return Error();
 }
@@ -318,25 +364,39 @@ static bool parseHex4(const std::string &s, uint32_t &v) {
     return true;
 }
 
-// getDeviceName, device_plugin.go:208-259.  "" means "not found" exactly like the reference;
-// sysfs ids are four lowercase hex digits, anything else is treated as not found.
-std::string Plugin::getDeviceName(const std::string &deviceID) {
+// getDeviceName, device_plugin.go:208-259, for a whole batch of device ids: ONE join and ONE name
+// gather through the ABI (cgo calls stay coarse).  "" means "not found" exactly like the
+// reference; sysfs ids are four lowercase hex digits, anything else is treated as not found.
+std::vector<std::string> Plugin::getDeviceNames(const std::vector<std::string> &deviceIDs) {
+    std::vector<std::string> out(deviceIDs.size());
     Error e = ensureTable();
-    if (e) { fprintf(stderr, "%s\n", e.message.c_str()); return ""; }  // :211-214
-    uint32_t d;
-    if (!parseHex4(deviceID, d)) return "";
-    uint32_t key = (0x10deu << 16) | d;  // nvidiaVendorID, :19
-    int32_t row = KXPU_ROW_MISS;
-    if (kxpu_lookup(ctx_, table_, &key, 1, &row) != KXPU_OK || row == KXPU_ROW_MISS) {
-        fprintf(stderr, "Could not find NVIDIA device with id: %s\n", deviceID.c_str());  // :234
-        return "";
+    if (e) { fprintf(stderr, "%s\n", e.message.c_str()); return out; }  // :211-214
+    std::vector<uint32_t> keys;
+    std::vector<size_t> where;
+    for (size_t i = 0; i < deviceIDs.size(); i++) {
+        uint32_t d;
+        if (parseHex4(deviceIDs[i], d)) { keys.push_back((0x10deu << 16) | d); where.push_back(i); }  // nvidiaVendorID, :19
     }
-    uint8_t name[65536];
-    uint32_t offs[2];
+    if (keys.empty()) return out;
+    std::vector<int32_t> rows(keys.size(), KXPU_ROW_MISS);
+    if (kxpu_lookup(ctx_, table_, keys.data(), keys.size(), rows.data()) != KXPU_OK) return out;
+    std::vector<uint32_t> offs(keys.size() + 1);
     size_t need = 0;
-    if (kxpu_names(ctx_, table_, &row, 1, name, sizeof name, offs, &need) != KXPU_OK) return "";
-    return std::string((const char *)name, need);
+    int32_t rc = kxpu_names(ctx_, table_, rows.data(), rows.size(), nullptr, 0, offs.data(), &need);
+    if (rc != KXPU_OK && rc != KXPU_E_NOSPACE) return out;
+    std::vector<uint8_t> blob(need ? need : 1);
+    if (need && kxpu_names(ctx_, table_, rows.data(), rows.size(), blob.data(), need, offs.data(), &need) != KXPU_OK) return out;
+    for (size_t k = 0; k < keys.size(); k++) {
+        if (rows[k] == KXPU_ROW_MISS) {
+            fprintf(stderr, "Could not find NVIDIA device with id: %s\n", deviceIDs[where[k]].c_str());  // :234
+            continue;
+        }
+        out[where[k]].assign((const char *)blob.data() + offs[k], offs[k + 1] - offs[k]);
+    }
+    return out;
 }
+
+std::string Plugin::getDeviceName(const std::string &deviceID) { return getDeviceNames({deviceID})[0]; }
 
 // generateCDISpec, device_plugin.go:55-80 + CdiSpec.Save, cdi/spec.go:85-127
 Error Plugin::generateCDISpec(const OrderedMap<std::vector<NvidiaGpuDevice>> &m, const std::string &format) {
@@ -377,10 +437,14 @@ Error Plugin::generateCDISpec(const OrderedMap<std::vector<NvidiaGpuDevice>> &m,
 // createDevicePlugins, device_plugin.go:83-112 (nothing is started: no gRPC here)
 Error Plugin::createDevicePlugins() {
     devicePlugins.clear();
+    std::vector<std::string> ids;
+    for (const auto &kv : deviceMap) ids.push_back(kv.first);
+    const std::vector<std::string> names = getDeviceNames(ids);  // :99 for every device id at once
+    size_t at = 0;
     for (const auto &kv : deviceMap) {  // :91
         GenericDevicePlugin dp;
         for (const std::string &dev : kv.second) dp.devs.push_back(Device{dev, kHealthy});  // :93-98
-        std::string devpluginName = getDeviceName(kv.first);                                // :99
+        std::string devpluginName = names[at++];
         if (devpluginName.empty()) {
             fprintf(stderr, "Error: Could not find device name for device id: %s\n", kv.first.c_str());
             devpluginName = kv.first;  // :100-103
@@ -399,16 +463,6 @@ Error Plugin::InitiateDevicePlugin() {
     e = generateCDISpec(iommuMap);  // :49
     if (e) return e;
     return createDevicePlugins();  // :52
-}
-
-// the Trim half of readIDFromFileFunc (:189) for the Allocate re-validation, which compares one
-// freshly read vendor file per allocated device (generic_device_plugin.go:334)
-static std::string trimID(const std::string &raw) {
-    if (raw.size() < 2) return std::string();
-    size_t a = 2, b = raw.size();
-    while (a < b && raw[a] == '\n') a++;
-    while (b > a && raw[b - 1] == '\n') b--;
-    return raw.substr(a, b - a);
 }
 
 // Allocate, generic_device_plugin.go:320-355, for one ContainerAllocateRequest

@@ -112,6 +112,8 @@ class Plugin {
     Error createIommuDeviceMap();
     // device_plugin.go:208-259: parse-once table + batched lookup + sanitiser on the GPU (S2)
     std::string getDeviceName(const std::string &deviceID);
+    // the same for a batch of ids: one kxpu_lookup + one kxpu_names (device_plugin.go:99 for every id of deviceMap)
+    std::vector<std::string> getDeviceNames(const std::vector<std::string> &deviceIDs);
     // device_plugin.go:55-80 + cdi/spec.go:85-127: emit on the GPU, host writes the file (S3)
     Error generateCDISpec(const OrderedMap<std::vector<NvidiaGpuDevice>> &m, const std::string &format = "YAML");
     // device_plugin.go:83-112: per device id device lists + plugin objects (S4); nothing is started

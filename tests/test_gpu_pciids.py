@@ -355,3 +355,31 @@ def test_every_range_length(rch, oracle, pci_text, monkeypatch):
             check_text(k, oracle, pci_text[:n])
     finally:
         k.close()
+
+
+def test_name_lengths_around_the_finalize_windows(kx, oracle):
+    """The finalize looks at a 128-byte window per row (fast path), stages up to ~1 KB for longer lines
+    (warp path) and reads even longer ones serially: names of every length around those limits, at
+    every 16-byte phase of the line start, with trailing CR / blanks / non-ASCII bytes."""
+    rng = np.random.default_rng(3)
+    alphabet = np.frombuffer(b"abcXYZ019 /._-[]()\t", np.uint8)
+    parts, keys = [b"1234  Vendor\n"], []
+    d = 0
+    for ln in list(range(0, 20)) + list(range(100, 135)) + list(range(980, 1040)) + [2000, 5000]:
+        for pad in (0, 3, 7, 13):
+            name = alphabet[rng.integers(0, len(alphabet), ln)].tobytes()
+            tail = [b"", b"\r", b"  ", b" \xc2\xa0"][(ln + pad) % 4]
+            parts.append(b"#" + b"x" * pad + b"\n")  # shifts the 16-byte phase of the next line
+            parts.append(b"\t%04x  " % d + name + tail + b"\n")
+            keys.append(0x12340000 | d)
+            d += 1
+    text = b"".join(parts)
+    tab = kx.pciids_load(text)
+    try:
+        r = kx.lookup(tab, np.array(keys, np.uint32))
+        assert (r >= 0).all()
+        names, _, _ = kx.names(tab, r)
+        for k, nm in zip(keys, names):
+            assert nm == (oracle.device_name(text, k)[1] or b""), hex(k)
+    finally:
+        tab.free()

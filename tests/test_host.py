@@ -260,16 +260,26 @@ def test_fast_gather_equals_walk(tmp_path, threads):
 
 
 def test_fast_gather_error_behaviour_equals_walk(tmp_path):
-    """A non-canonical iommu_group aborts the walk at that entry (the records before it stay)."""
-    from kxpu_b200.binding import DEVREC_DTYPE
+    """An entry the record cannot carry (non-canonical iommu_group of an NVIDIA vfio-pci function) is
+    skipped like a read error -- flag KXPU_REC_IOMMU_ERR -- and never stops the walk; both gathers agree.
+    On entries the reference would not accept anyway (other vendor / driver) nothing is read at all."""
+    from kxpu_b200.binding import DEVREC_DTYPE, REC_IOMMU_ERR
     devs = _synthetic_devices(300, 5)
+    for d in devs[198:203]:
+        d.update(vendor=b"0x10de\n", driver="vfio-pci", device=b"0x2330\n", group=90)
+    devs[201].update(vendor=b"0x8086\n")
     base = fake_sysfs.make_tree(str(tmp_path), devs)
-    victim = os.path.join(base, devs[200]["bdf"], "iommu_group")
-    if os.path.lexists(victim):
-        os.remove(victim)
-    os.symlink("/somewhere/not-a-number", victim)
-    for fn, kw in ((fake_sysfs.gather, {}), (fake_sysfs.gather_fast, dict(threads=4))):
-        with pytest.raises(RuntimeError, match="not a canonical decimal"):
-            fn(base, DEVREC_DTYPE, **kw)
+    for k in (200, 201):  # 200: NVIDIA + vfio-pci -> skipped with a log; 201: other vendor -> the link is never read
+        victim = os.path.join(base, devs[k]["bdf"], "iommu_group")
+        if os.path.lexists(victim):
+            os.remove(victim)
+        os.symlink("/somewhere/not-a-number", victim)
+    slow = fake_sysfs.gather(base, DEVREC_DTYPE)
+    fast = fake_sysfs.gather_fast(base, DEVREC_DTYPE, threads=4)
+    assert slow.tobytes() == fast.tobytes() and len(slow) >= 300
+    by_bdf = {r["bdf"]: r for r in slow}
+    assert by_bdf[devs[200]["bdf"].encode()]["flags"] & REC_IOMMU_ERR
+    assert by_bdf[devs[199]["bdf"].encode()]["flags"] == 0 and by_bdf[devs[202]["bdf"].encode()]["flags"] == 0
+    assert by_bdf[devs[201]["bdf"].encode()]["flags"] == 0 and by_bdf[devs[201]["bdf"].encode()]["driver"] == b""
     with pytest.raises(RuntimeError):
         fake_sysfs.gather_fast(str(tmp_path / "missing"), DEVREC_DTYPE)
