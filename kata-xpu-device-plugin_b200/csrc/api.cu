@@ -420,14 +420,13 @@ int32_t kx_launch_trunc(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, siz
 }
 
 int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base,
-                           const unsigned long long *vendor_first, const unsigned long long *trunc, const kxx::WaitSpec *wait,
-                           const KxSlabOut *slab) {
+                           const kxx::MinView *mv, const kxx::WaitSpec *wait, const KxSlabOut *slab) {
     kxparse::FinalizeParams F;
     memset(&F, 0, sizeof F);
     if (wait) F.wait = *wait;
     F.text = d_text; F.n = n; F.base = base; F.tab = t->dev;
-    F.vendor_first = vendor_first ? vendor_first : t->dev.vendor_first;
-    F.trunc = trunc ? trunc : t->dev.trunc;
+    if (mv) F.mv = *mv;
+    else { F.mv.a = t->dev.vendor_first; F.mv.stride = 0; F.mv.n = 1; F.mv.trunc1 = t->dev.trunc; }
     F.row_key = t->row_key; F.row_line = t->row_line; F.row_anchor = t->row_anchor;
     F.row_name_off = t->row_name_off; F.row_name_len = t->row_name_len;
     F.blob = t->blob; F.blob_cap = t->blob_cap;
@@ -484,7 +483,7 @@ static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t 
         // a text with a >= 2 KiB stretch without a newline was seen on an earlier attempt: the exact
         // bufio.ErrTooLong cut-off is computed before the finalize
         if (rc == KXPU_OK && have_trunc) rc = kx_launch_trunc(ctx, t, d_text, n, 0);
-        if (rc == KXPU_OK) rc = kx_launch_finalize(ctx, t, d_text, n, 0, nullptr, nullptr, nullptr, nullptr);
+        if (rc == KXPU_OK) rc = kx_launch_finalize(ctx, t, d_text, n, 0, nullptr, nullptr, nullptr);
         // the join does not need anything from the host: enqueue it before the round trip below
         // (it is simply run again if the table has to be rebuilt)
         if (rc == KXPU_OK && join) rc = kx_launch_lookup(ctx, t, join->d_keys, join->n, join->d_rows);

@@ -30,7 +30,7 @@ struct __align__(16) GSlot { uint32_t key, first, ord, pad; };                //
 struct __align__(16) DSlot { unsigned long long key; uint32_t first, ord; };  // device id string -> first group-first record, ordinal
 
 constexpr int C_THREADS = 256;
-constexpr int C_ITEMS = 16;
+constexpr int C_ITEMS = 8;
 constexpr int C_TILE = C_THREADS * C_ITEMS;  // records per CTA of the scan kernels
 
 // totals[] (device): 0 accepted, 1 groups, 2 device ids, 3 unsupported-input flag
@@ -39,7 +39,7 @@ struct Work {
     uint32_t n;
     GSlot *gtab;
     DSlot *dtab;
-    uint32_t gcap, gshift;
+    uint32_t gcap, gshift, dcap, dshift;
     uint32_t *gslot;      // [n] slot of the record's group (EMPTY32: not a candidate)
     uint32_t *grp_rec;    // [n_groups] first record of group ordinal o
     uint32_t *grp_dslot;  // [n_groups] device-id slot of group ordinal o
@@ -87,17 +87,21 @@ __device__ __forceinline__ uint32_t ginsert(const Work &W, uint32_t key) {
         slot = (slot + 1) & (W.gcap - 1);
     }
 }
+// the device-id table starts small (real hosts see a few ids; a 4-hex id space holds 65 536): a probe
+// run of 512 means it is too small -- flag it (totals[3] bit 1), the host runs again with dcap = gcap
 __device__ __forceinline__ uint32_t dinsert(const Work &W, unsigned long long key) {
-    uint32_t slot = hash64(key) >> W.gshift;
-    for (;;) {
+    uint32_t slot = hash64(key) >> W.dshift;
+    for (uint32_t step = 0; step < 512u; step++) {
         unsigned long long k = __ldcg(&W.dtab[slot].key);
         if (k == key) return slot;
         if (k == EMPTY64) {
             unsigned long long old = atomicCAS(&W.dtab[slot].key, EMPTY64, key);
             if (old == EMPTY64 || old == key) return slot;
         }
-        slot = (slot + 1) & (W.gcap - 1);
+        slot = (slot + 1) & (W.dcap - 1);
     }
+    atomicOr(&W.totals[3], 2u);
+    return 0u;
 }
 
 // pass 1: candidates, group table, gfirst
@@ -120,18 +124,18 @@ __global__ void __launch_bounds__(256) k_candidates(const Work W) {
                 vid == 0x65643031ull /* "10de" */ && !(fl & KXPU_REC_DRIVER_ERR) &&
                 drv0 == 0x6963702d6f696676ull /* "vfio-pci" */ && drv8 == 0u && !(fl & KXPU_REC_IOMMU_ERR);
     bool dok = !(fl & KXPU_REC_DEVICE_ERR) && read_id(dtxt, dlen, did, dl);
-    if (!(fl & (KXPU_REC_IS_DIR | KXPU_REC_VENDOR_ERR)) && vlen > 8u) W.totals[3] = 1u;
+    if (!(fl & (KXPU_REC_IS_DIR | KXPU_REC_VENDOR_ERR)) && vlen > 8u) atomicOr(&W.totals[3], 1u);
     if (cand && (group == EMPTY32 || (dok && did == EMPTY64) || (!(fl & KXPU_REC_DEVICE_ERR) && dlen > 8u)))
-        W.totals[3] = 1u;  // outside the supported domain
+        atomicOr(&W.totals[3], 1u);  // outside the supported domain
     uint32_t slot = EMPTY32;
     if (cand) {
         slot = ginsert(W, group);
-        if (dok) atomicMin(&W.gtab[slot].first, i);
+        if (dok && i < __ldcg(&W.gtab[slot].first)) atomicMin(&W.gtab[slot].first, i);
     }
     W.gslot[i] = slot;
 }
 
-// pass 2: accept / group-first flags of a 4096-record tile, both exclusive scans in the same kernel
+// pass 2: accept / group-first flags of a 2048-record tile, both exclusive scans in the same kernel
 // (two look-backs, warp 0 and warp 1), busIndex out, group ordinals out, device-id table insert.
 __global__ void __launch_bounds__(C_THREADS) k_accept_scan(const Work W) {
     __shared__ uint32_t wsum[C_THREADS / 32];
@@ -151,15 +155,17 @@ __global__ void __launch_bounds__(C_THREADS) k_accept_scan(const Work W) {
         for (int k = 0; k < C_ITEMS; k++) slot[k] = base + k < W.n ? W.gslot[base + k] : EMPTY32;
     }
     uint32_t accm = 0, gfm = 0;  // bit k: record base + k accepted / first of its group
+    uint32_t first[C_ITEMS];
+#pragma unroll
+    for (int k = 0; k < C_ITEMS; k++) first[k] = W.gtab[slot[k] != EMPTY32 ? slot[k] : 0u].first;  // all loads in flight at once
 #pragma unroll
     for (int k = 0; k < C_ITEMS; k++) {
         if (slot[k] != EMPTY32) {
-            const uint32_t first = W.gtab[slot[k]].first;
-            if (first <= base + k) accm |= 1u << k;
-            if (first == base + k) gfm |= 1u << k;
+            if (first[k] <= base + k) accm |= 1u << k;
+            if (first[k] == base + k) gfm |= 1u << k;
         }
     }
-    const uint32_t packed = (uint32_t)__popc(accm) | ((uint32_t)__popc(gfm) << 16);  // <= 4096 each per tile
+    const uint32_t packed = (uint32_t)__popc(accm) | ((uint32_t)__popc(gfm) << 16);  // <= 2048 each per tile
     const uint32_t incl = kxscan::warp_incl(packed);
     if (lane == 31) wsum[w] = incl;
     __syncthreads();
@@ -201,7 +207,9 @@ __global__ void __launch_bounds__(C_THREADS) k_accept_scan(const Work W) {
             uint32_t dl;
             read_id(reinterpret_cast<const uint8_t *>(&dq), dlen, did, dl);
             const uint32_t ds = dinsert(W, did);
-            atomicMin(&W.dtab[ds].first, i);
+            // a few hot device ids own most groups: same-address atomics run at ~1 per ns, so only a record that
+            // can still lower the minimum issues one (the early tiles settle it, the rest only load)
+            if (i < __ldcg(&W.dtab[ds].first)) atomicMin(&W.dtab[ds].first, i);
             W.grp_dslot[ord] = ds;
         }
     }
@@ -280,15 +288,15 @@ __global__ void __launch_bounds__(256) k_pairs(const Work W, uint32_t passes) {
 }
 
 // ---------------------------------------------------------------- stable LSD radix sort, one kernel per pass
-// A CTA ranks a tile of 8192 pairs: every warp owns 512 consecutive items and counts digits in its
+// A CTA ranks a tile of 4096 pairs: every warp owns 256 consecutive items and counts digits in its
 // own shared-memory counters (rank inside the warp by __match_any_sync), the warps' counts are
 // scanned per digit, the tile's count of every digit is published and the digit's offset over the
 // tiles in front comes from a look-back over those status words (one digit per thread), the
 // pass-wide digit bases from the histogram k_pairs made.  Both sorts run in the same launch.
 constexpr int OS_WARPS = 16;
 constexpr int OS_THREADS = OS_WARPS * 32;
-constexpr int OS_STEPS = 16;
-constexpr int OS_TILE = OS_THREADS * OS_STEPS;  // 8192
+constexpr int OS_STEPS = 8;
+constexpr int OS_TILE = OS_THREADS * OS_STEPS;  // 4096
 
 struct SortJob {
     const uint32_t *kin, *vin;
@@ -421,12 +429,22 @@ static uint32_t bits_for(uint32_t n) {
     return b;
 }
 
+static int32_t classify_once(kxpu_ctx *ctx, const kxpu_devrec *recs, size_t n, kxpu_classify_out *out, bool small_dtab, bool *retry);
+
 extern "C" int32_t kxpu_classify(kxpu_ctx *ctx, const kxpu_devrec *recs, size_t n, kxpu_classify_out *out) {
     if (!ctx || !out || (n && !recs)) return KXPU_E_INVALID;
     if (n >= 0x7FFFFFFFull) return KXPU_E_UNSUPPORTED;
     std::lock_guard<std::mutex> guard(ctx->mu);
     cudaSetDevice(ctx->device);
     kx_clear_timings(ctx);
+    bool retry = false;
+    int32_t rc = classify_once(ctx, recs, n, out, true, &retry);
+    if (retry) rc = classify_once(ctx, recs, n, out, false, &retry);  // more distinct device ids than the small table holds
+    return rc;
+}
+
+static int32_t classify_once(kxpu_ctx *ctx, const kxpu_devrec *recs, size_t n, kxpu_classify_out *out, bool small_dtab, bool *retry) {
+    *retry = false;
     out->n_accepted = out->n_groups = out->n_devids = 0;
     if (n == 0) {
         if (out->group_off) out->group_off[0] = 0;
@@ -442,6 +460,9 @@ extern "C" int32_t kxpu_classify(kxpu_ctx *ctx, const kxpu_devrec *recs, size_t 
     while (gcap < 2 * N) gcap <<= 1;
     uint32_t lg = 0;
     while ((1u << lg) < gcap) lg++;
+    const uint32_t dcap = small_dtab ? std::min<uint32_t>(gcap, 1u << 17) : gcap;
+    uint32_t dlg = 0;
+    while ((1u << dlg) < dcap) dlg++;
     const uint32_t c_tiles = (N + C_TILE - 1) / C_TILE;
     const uint32_t s_tiles = (N + OS_TILE - 1) / OS_TILE;
     const uint32_t passes = (bits_for(N) + 7) / 8;
@@ -449,7 +470,7 @@ extern "C" int32_t kxpu_classify(kxpu_ctx *ctx, const kxpu_devrec *recs, size_t 
     // one arena; [ff-region | zero-region | rest]
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
-    const size_t o_gtab = take((size_t)gcap * sizeof(GSlot)), o_dtab = take((size_t)gcap * sizeof(DSlot));
+    const size_t o_gtab = take((size_t)gcap * sizeof(GSlot)), o_dtab = take((size_t)dcap * sizeof(DSlot));
     const size_t ff_bytes = off;
     const size_t o_totals = take(16), o_ghist = take(2 * 4 * 256 * 4);
     const size_t zero_words = (off - ff_bytes) / 4;
@@ -470,7 +491,7 @@ extern "C" int32_t kxpu_classify(kxpu_ctx *ctx, const kxpu_devrec *recs, size_t 
     Work W;
     memset(&W, 0, sizeof W);
     W.recs = (const kxpu_devrec *)(b + o_recs); W.n = N;
-    W.gtab = (GSlot *)(b + o_gtab); W.dtab = (DSlot *)(b + o_dtab); W.gcap = gcap; W.gshift = 32 - lg;
+    W.gtab = (GSlot *)(b + o_gtab); W.dtab = (DSlot *)(b + o_dtab); W.gcap = gcap; W.gshift = 32 - lg; W.dcap = dcap; W.dshift = 32 - dlg;
     W.gslot = (uint32_t *)(b + o_gslot); W.grp_rec = (uint32_t *)(b + o_grec); W.grp_dslot = (uint32_t *)(b + o_gds);
     W.totals = (uint32_t *)(b + o_totals); W.ghist = (uint32_t *)(b + o_ghist);
     W.st_acc = st; W.st_gf = st + c_tiles; W.st_df = st + 2 * (size_t)c_tiles;
@@ -514,7 +535,9 @@ extern "C" int32_t kxpu_classify(kxpu_ctx *ctx, const kxpu_devrec *recs, size_t 
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     int32_t rc = KXPU_OK;
     if (e != cudaSuccess) { KX_SET_ERR(ctx, "classify failed: %s", cudaGetErrorString(e)); rc = KXPU_E_CUDA; }
-    else if (h[3]) { KX_SET_ERR(ctx, "classify: record outside the supported domain (group 0xffffffff or id file > 8 bytes)"); rc = KXPU_E_UNSUPPORTED; }
+    else if ((h[3] & 2u) && small_dtab) { *retry = true; return KXPU_E_CAPACITY; }
+    else if (h[3] & 1u) { KX_SET_ERR(ctx, "classify: record outside the supported domain (group 0xffffffff or id file > 8 bytes)"); rc = KXPU_E_UNSUPPORTED; }
+    else if (h[3] & 2u) { KX_SET_ERR(ctx, "classify: device-id table overflow"); rc = KXPU_E_CAPACITY; }
     if (rc == KXPU_OK) {
         const uint32_t na = h[0], ng = h[1], nd = h[2];
         out->n_accepted = na; out->n_groups = ng; out->n_devids = nd;

@@ -6,11 +6,14 @@
 // line of the shard and for every vendor prefix its earliest anchor.  "First anchor wins"
 // (device_plugin.go:263-267) is then decided across shards in two exchange phases:
 //
-//   A  all-reduce(min) of vendor_first (+ the bufio.ErrTooLong cut-off and status bits): every
-//      rank atomicMin's its local minima straight into every rank's exchange region over NVLink
-//      (peer-memory stores; ~2 400 x 8 B per rank for pci.ids).  After phase A every rank knows
-//      the global first anchor of every vendor id, so a row is a WINNER iff its anchor equals
-//      it -- and winners are globally unique per key (the first block sits in exactly one shard).
+//   A  all-reduce(min) of vendor_first (+ the bufio.ErrTooLong cut-off and status bits), done as an
+//      all-gather with the min taken by the reader: every rank stores its dense first-anchor array
+//      (512 KB, plain 16-byte stores over NVLink -- remote 64-bit atomics cost ~10 ns apiece, the
+//      copy is one streaming write) into ITS block of every rank's exchange region; nothing is ever
+//      cleared, the block is overwritten whole each epoch.  After phase A every rank knows the
+//      global first anchor of every vendor id (min over the R blocks), so a row is a WINNER iff
+//      its anchor equals it -- and winners are globally unique per key (the first block sits in
+//      exactly one shard).
 //   B  winners only: each rank sanitises the names of its winner rows and pushes rows + names
 //      into its slab in every rank's region.  Shards that hold no first block push nothing.
 //      Every rank then inserts the winners of all ranks into the table it parsed into -- no
@@ -19,15 +22,15 @@
 //      result buffer: the all-gather of hits rides on the probe kernel.
 //
 // A phase boundary is a flag per (phase, buffer, rank) in every region, raised by the last CTA
-// of the pushing kernel after a system fence, and a one-warp wait kernel.  Two buffers alternate
-// by epoch; a buffer is cleared one epoch ahead, before this rank raises the flag that lets its
-// peers move on (so a peer can never push into a buffer that is still being cleared or read).
+// of the pushing kernel after a system fence, and a wait in the prologue of the consumer kernel (a
+// one-warp wait kernel when several contexts share a GPU).  Two buffers alternate by epoch: a rank
+// can only start epoch e + 2 after every peer delivered e + 1, i.e. finished reading epoch e.
 // The epoch is bumped before anything can fail, statuses travel WITH the data (min-encoded words
 // in phase A, slab headers in phase B), so every rank takes the same retry decision; a time-out
 // or a CUDA error marks the exchange broken (re-init required).
 //
 // Transports: peer memory (CUDA IPC mappings across processes, direct pointers inside one
-// process) is the product path; NCCL (ncclAllReduce(min) / ncclAllGather, loaded lazily with
+// process) is the product path; NCCL (ncclAllGather for every phase, loaded lazily with
 // dlopen) runs the same kernels against a local staging region when peer mapping is impossible
 // (KXPU_NO_P2P=1 forces it) or a slab outgrows the fixed peer region.
 #include <dlfcn.h>
@@ -45,7 +48,6 @@ namespace kxx {
 typedef int (*fn_get_unique_id)(void *);
 typedef int (*fn_comm_destroy)(void *);
 typedef int (*fn_all_gather)(const void *, void *, size_t, int, void *, cudaStream_t);
-typedef int (*fn_all_reduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef const char *(*fn_err_string)(int);
 struct UniqueId { char internal[128]; };
 typedef int (*fn_comm_init_rank)(void **, int, UniqueId, int);  // ncclUniqueId is passed by value (128 bytes)
@@ -56,12 +58,11 @@ struct NcclApi {
     fn_comm_init_rank comm_init_rank = nullptr;
     fn_comm_destroy comm_destroy = nullptr;
     fn_all_gather all_gather = nullptr;
-    fn_all_reduce all_reduce = nullptr;
     fn_err_string err_string = nullptr;
 };
 static NcclApi g_nccl;
 static std::mutex g_nccl_mu;
-constexpr int NCCL_UINT8 = 1, NCCL_UINT64 = 5, NCCL_MIN = 3;
+constexpr int NCCL_UINT8 = 1;
 
 static bool nccl_load() {
     std::lock_guard<std::mutex> g(g_nccl_mu);
@@ -77,9 +78,8 @@ static bool nccl_load() {
     g_nccl.comm_init_rank = (fn_comm_init_rank)dlsym(h, "ncclCommInitRank");
     g_nccl.comm_destroy = (fn_comm_destroy)dlsym(h, "ncclCommDestroy");
     g_nccl.all_gather = (fn_all_gather)dlsym(h, "ncclAllGather");
-    g_nccl.all_reduce = (fn_all_reduce)dlsym(h, "ncclAllReduce");
     g_nccl.err_string = (fn_err_string)dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.comm_destroy || !g_nccl.all_gather || !g_nccl.all_reduce) return false;
+    if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.comm_destroy || !g_nccl.all_gather) return false;
     g_nccl.handle = h;
     return true;
 }
@@ -90,13 +90,14 @@ constexpr size_t FLAGS_BYTES = 1024;  // u32 flag[3 phases][2 buffers][KX_MAX_RA
 struct XCaps { uint32_t rows, blob, join; };  // per-rank slab rows / name bytes, keys of one sharded join
 
 struct XLayout {
-    size_t o_a[2], o_slab[2], slab_stride, o_res[2], total;
+    size_t o_a[2], a_stride, o_slab[2], slab_stride, o_res[2], total;  // o_a[b]: phase-A block of rank 0, rank r at + r * a_stride
 };
 __host__ __device__ static inline size_t x_align(size_t x) { return (x + 255) / 256 * 256; }
 static XLayout x_layout(const XCaps &c, int R) {
     XLayout L;
     size_t off = FLAGS_BYTES;
-    for (int b = 0; b < 2; b++) { L.o_a[b] = off; off = x_align(off + (size_t)A_WORDS * 8); }
+    L.a_stride = x_align((size_t)A_WORDS * 8);
+    for (int b = 0; b < 2; b++) { L.o_a[b] = off; off += (size_t)R * L.a_stride; }
     L.slab_stride = x_align(sizeof(SlabHeader) + (size_t)c.rows * sizeof(SlabRow) + c.blob + 16);
     for (int b = 0; b < 2; b++) { L.o_slab[b] = off; off += (size_t)R * L.slab_stride; }
     for (int b = 0; b < 2; b++) { L.o_res[b] = off; off = x_align(off + (size_t)c.join * 4); }
@@ -208,7 +209,7 @@ struct MergeParams {
     size_t stride;
     int R;
     uint32_t slab_rows_cap;
-    const unsigned long long *a;  // my phase-A block (status words)
+    MinView mv;  // the phase-A blocks of all ranks (status words)
     KxTableDev tab;
     uint32_t *row_key, *row_name_off, *row_name_len;
     unsigned long long *row_line, *row_anchor;
@@ -226,9 +227,7 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeParams P) {
     __shared__ uint32_t rpre[KX_MAX_RANKS + 1], bpre[KX_MAX_RANKS + 1], s_status, s_maxkeys;
     wait_flags_cta(P.wait);
     if (threadIdx.x == 0) {
-        uint32_t st = 0, mk = 0, racc = 0, bacc = 0;
-        for (int k = 0; k < XS_BITS; k++)
-            if (P.a[A_STATUS0 + k] == 0ull) st |= 1u << k;
+        uint32_t st = min_view_status(P.mv), mk = 0, racc = 0, bacc = 0;
         for (int r = 0; r < P.R; r++) {
             const SlabHeader *h = reinterpret_cast<const SlabHeader *>(P.slabs + (size_t)r * P.stride);
             rpre[r] = racc; bpre[r] = bacc;
@@ -339,19 +338,12 @@ __global__ void __launch_bounds__(256) gather_copy_kernel(const WaitSpec W, cons
     if (blockIdx.x == 0 && threadIdx.x < n_tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
 }
 
-__global__ void fill_ff_kernel(uint4 *p, size_t n16) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
-        p[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-}
-
 // ------------------------------------------------------------------ region set-up
 static int32_t region_alloc(kxpu_ctx *ctx, KxExchange *x, const XCaps &caps) {
     x->caps = caps;
     x->L = x_layout(caps, x->nranks);
     if (cudaMalloc((void **)&x->local, x->L.total) != cudaSuccess) { cudaGetLastError(); x->local = nullptr; return KXPU_E_NOMEM; }
     bool ok = cudaMemsetAsync(x->local, 0, FLAGS_BYTES, ctx->stream) == cudaSuccess;
-    for (int b = 0; b < 2 && ok; b++) ok = cudaMemsetAsync(x->local + x->L.o_a[b], 0xff, (size_t)A_WORDS * 8, ctx->stream) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&x->scratch, 256) == cudaSuccess && cudaMemsetAsync(x->scratch, 0, 256, ctx->stream) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     if (!ok) { cudaGetLastError(); return KXPU_E_CUDA; }
@@ -540,8 +532,6 @@ static void shard_phase1(ShardOp &op) {
         if (x->scaps.blob > want.blob) want.blob = x->scaps.blob;
         op.rc = stage_reserve(ctx, x, want);
         if (op.rc != KXPU_OK) return;
-        fill_ff_kernel<<<64, 256, 0, ctx->stream>>>((uint4 *)(x->stage + x->SL.o_a[0]), (size_t)A_WORDS * 8 / 16);
-        KX_LAUNCHED(ctx);
     }
     const uint32_t num_chunks = (uint32_t)((op.a.n + kxparse::CW - 1) / kxparse::CW);
     op.rc = kx_table_acquire(ctx, x->x_cap, x->x_blob_cap, num_chunks, &op.t);
@@ -559,8 +549,7 @@ static void shard_phase1(ShardOp &op) {
     memset(&hook, 0, sizeof hook);
     XaParams &P = hook.p;
     P.tg = targets(op);
-    P.mine = my_region(op);
-    P.o_a = L.o_a[op.b]; P.o_a_next = L.o_a[op.b ^ 1]; P.clear_next = op.nccl ? 0 : 1;
+    P.o_a = L.o_a[op.b] + (size_t)x->rank * L.a_stride;  // my block (of this buffer) in every region
     P.o_flag = flag_off(0, op.b, x->rank); P.raise_flags = op.nccl ? 0 : 1; P.epoch = op.epoch;
     P.vendor_first = t->dev.vendor_first; P.trunc = t->dev.trunc; P.counters = t->dev.counters;
     P.max_keys = t->dev.max_keys; P.have_trunc = op.have_trunc ? 1 : 0;
@@ -580,9 +569,9 @@ static void shard_phase2(ShardOp &op) {
     uint8_t *mine = my_region(op);
     WaitSpec ws{nullptr, x->nranks, op.epoch, x->scratch + 8};
     if (op.nccl) {
-        unsigned long long *a = reinterpret_cast<unsigned long long *>(mine + L.o_a[0]);
-        const int nrc = g_nccl.all_reduce(a, a, (size_t)A_WORDS, NCCL_UINT64, NCCL_MIN, ctx->nccl_comm, ctx->stream);
-        if (nrc != 0) { nccl_fail(op, "ncclAllReduce(min)", nrc); return; }
+        uint8_t *a0 = mine + L.o_a[0];  // the R phase-A blocks are contiguous: in-place all-gather of mine
+        const int nrc = g_nccl.all_gather(a0 + (size_t)x->rank * L.a_stride, a0, L.a_stride, NCCL_UINT8, ctx->nccl_comm, ctx->stream);
+        if (nrc != 0) { nccl_fail(op, "ncclAllGather(phase A)", nrc); return; }
     } else {
         ws.flags = reinterpret_cast<const uint32_t *>(mine + flag_off(0, op.b, 0));
         if (!x->fuse_waits) {
@@ -592,12 +581,12 @@ static void shard_phase2(ShardOp &op) {
         }
     }
     g_trace.mark(3, ctx->stream);
-    const unsigned long long *a = reinterpret_cast<const unsigned long long *>(mine + L.o_a[op.b]);
-    // winners (judged against the all-reduced minima) are sanitised straight into my own slab
+    const MinView mv{reinterpret_cast<const unsigned long long *>(mine + L.o_a[op.b]), L.a_stride / 8, x->nranks, nullptr};
+    // winners (judged against the minima over all ranks' blocks) are sanitised straight into my own slab
     const uint32_t rows_cap = op.nccl ? x->scaps.rows : x->caps.rows, blob_cap = op.nccl ? x->scaps.blob : x->caps.blob;
     uint8_t *own_slab = op.nccl ? x->send_slab : mine + L.o_slab[op.b] + (size_t)x->rank * L.slab_stride;
     KxSlabOut so{own_slab + slab_rows_off(), rows_cap, own_slab + slab_blob_off(rows_cap), blob_cap};
-    op.rc = kx_launch_finalize(ctx, t, op.a.d_text, op.a.n, op.a.base, a, a + A_TRUNC, &ws, &so);
+    op.rc = kx_launch_finalize(ctx, t, op.a.d_text, op.a.n, op.a.base, &mv, &ws, &so);
     if (op.rc != KXPU_OK) return;
     g_trace.mark(4, ctx->stream);
     XbParams P;
@@ -638,7 +627,7 @@ static void shard_phase3(ShardOp &op) {
     M.wait = ws;
     M.slabs = mine + L.o_slab[op.b]; M.stride = L.slab_stride; M.R = x->nranks;
     M.slab_rows_cap = op.nccl ? x->scaps.rows : x->caps.rows;
-    M.a = reinterpret_cast<const unsigned long long *>(mine + L.o_a[op.b]);
+    M.mv = MinView{reinterpret_cast<const unsigned long long *>(mine + L.o_a[op.b]), L.a_stride / 8, x->nranks, nullptr};
     M.tab = t->dev; M.row_key = t->row_key; M.row_name_off = t->row_name_off; M.row_name_len = t->row_name_len;
     M.row_line = t->row_line; M.row_anchor = t->row_anchor; M.blob = t->blob; M.rows_cap = t->rows_cap; M.blob_cap = t->blob_cap;
     M.timeout_flag = x->scratch + 8;

@@ -23,7 +23,8 @@ namespace kxemit {
 
 constexpr int TILE = 128;      // devices per CTA
 constexpr int EMIT_THREADS = 256;
-constexpr int MAX_FRAG = 384;  // upper bound of one fragment: literals (<= 292) + 2 x 20 + 2 x 10 + 15 + 2 + slack
+constexpr int MAX_FRAG = 368;  // upper bound of one fragment: literals (<= 284) + 2 x 20 + 2 x 10 + 15 + 2 + slack; with the rest of
+                               // TileSmem this keeps a CTA under 56.7 KB: four CTAs per SM, the 512 tiles of cfg5 are ONE wave
 constexpr int POOL_MAX = 640;
 
 // ------------------------------------------------------------------ templates
@@ -310,6 +311,7 @@ extern "C" int32_t kxpu_cdi_emit(kxpu_ctx *ctx, int32_t format, const kxpu_cdide
     const uint32_t N = (uint32_t)n;
     const uint32_t tiles = (N + TILE - 1) / TILE;
     const size_t bound = (size_t)n * (E.lit_total + 2 * 20 + 2 * 10 + 15 + 2 + 2) + E.len[6] + E.len[7] + 64;  // no fragment is longer
+    if (E.lit_total + 2 * 20 + 2 * 10 + 15 + 2 + 2 > (uint32_t)MAX_FRAG) return KXPU_E_INVALID;  // the literals grew: MAX_FRAG must follow
     KxScratch sc(ctx);
     kxpu_cdidev *d_devs = nullptr;
     uint8_t *d_out = nullptr;

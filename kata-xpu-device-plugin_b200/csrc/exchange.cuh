@@ -12,11 +12,44 @@ constexpr uint32_t XS_NEED_TRUNC = 2u;     // a rank saw a possible >= 64 KiB li
 constexpr uint32_t XS_SLAB_OVERFLOW = 4u;  // a rank's winners outgrow the slab
 constexpr uint32_t XS_GROW_BLOB = 8u;      // a rank's name blob is too small
 constexpr uint32_t XS_FULL = 16u;          // a rank's table ran completely full (its key count is unknown): grow faster
-constexpr int XS_BITS = 5;
 
-constexpr int A_TRUNC = 65536;    // phase-A block: u64 [65536] vendor_first | trunc | XS_BITS status words | pad
-constexpr int A_STATUS0 = 65537;  // status bit k is set iff word A_STATUS0 + k == 0 (so that min all-reduces it)
+// phase-A block of ONE source rank inside a region: u64 [65536] vendor_first | cut-off | status | pad.
+// Every rank owns one such block per buffer in every region and overwrites it completely each epoch
+// (plain 16-byte stores, nothing to clear, no remote atomics); consumers take the minimum over the
+// blocks of all ranks on the fly.
+constexpr int A_TRUNC = 65536;
+constexpr int A_STATUS = 65537;  // XS_* bits of the source rank (plain word)
 constexpr int A_WORDS = 65536 + 8;
+
+// the R phase-A blocks of one buffer as the consumers see them
+struct MinView {
+    const unsigned long long *a;  // block of rank 0 (single text: the table's own vendor_first, n = 1)
+    size_t stride;                // words between the blocks of consecutive ranks
+    int n;
+    const unsigned long long *trunc1;  // n == 1 only: the table's own cut-off word
+};
+__device__ __forceinline__ unsigned long long min_view_first(const MinView &V, uint32_t vendor) {
+    unsigned long long m = V.a[vendor];
+    for (int r = 1; r < V.n; r++) {
+        const unsigned long long x = V.a[(size_t)r * V.stride + vendor];
+        m = x < m ? x : m;
+    }
+    return m;
+}
+__device__ __forceinline__ unsigned long long min_view_trunc(const MinView &V) {
+    if (V.n == 1 && V.trunc1) return *V.trunc1;
+    unsigned long long m = KX_NO_OFF;
+    for (int r = 0; r < V.n; r++) {
+        const unsigned long long x = V.a[(size_t)r * V.stride + A_TRUNC];
+        m = x < m ? x : m;
+    }
+    return m;
+}
+__device__ __forceinline__ uint32_t min_view_status(const MinView &V) {
+    uint32_t st = 0;
+    for (int r = 0; r < V.n; r++) st |= (uint32_t)V.a[(size_t)r * V.stride + A_STATUS];
+    return st;
+}
 
 struct SlabHeader {  // 64 bytes
     uint32_t n_rows, blob_bytes, status, nkeys;
@@ -35,10 +68,8 @@ struct Targets {  // where a push goes: every rank's region (peer memory) or thi
 
 struct XaParams {
     Targets tg;
-    uint8_t *mine;         // my region (the next buffer's phase-A block is cleared here)
-    size_t o_a, o_a_next;  // phase-A block of this / the next epoch inside a region
-    int clear_next;
-    size_t o_flag;         // my phase-A flag inside a region (peer transport)
+    size_t o_a;     // my phase-A block inside a region
+    size_t o_flag;  // my phase-A flag inside a region (peer transport)
     int raise_flags;
     uint32_t epoch;
     const unsigned long long *vendor_first, *trunc;
@@ -47,20 +78,16 @@ struct XaParams {
     int have_trunc;
 };
 
-// Phase A: vendor_first / cut-off / status of this shard, min-reduced into every rank's region
-// (atomicMin over NVLink for the ~2 400 vendor ids a shard of pci.ids holds), then this rank's flag.
-// vendor_first is final before the last resolve kernel starts, so ALL its threads share the 65536
-// entries (xa_push_slice); cut-off, status and the flags wait for the CTA that finishes last
-// (xa_finish, thread 0 of that CTA, after every CTA's fence + counter).
+// Phase A: this shard's vendor_first (dense, 512 KB) goes into my block of every rank's region with
+// plain 16-byte stores over NVLink.  vendor_first is final before the last resolve kernel starts, so
+// ALL its threads share the copy (xa_push_slice); cut-off, status and the flags wait for the CTA that
+// finishes last (xa_finish, thread 0 of that CTA, after every CTA's fence + counter).
 __device__ __forceinline__ void xa_push_slice(const XaParams &P, uint32_t gtid, uint32_t gthreads) {
-    unsigned long long *nx = reinterpret_cast<unsigned long long *>(P.mine + P.o_a_next);
-    for (uint32_t v = gtid; v < 65536u; v += gthreads) {
-        const unsigned long long f = P.vendor_first[v];
-        if (P.clear_next) nx[v] = KX_NO_OFF;
-        if (f != KX_NO_OFF)
-            for (int q = 0; q < P.tg.n; q++) atomicMin(reinterpret_cast<unsigned long long *>(P.tg.region[q] + P.o_a) + v, f);
+    const uint4 *src = reinterpret_cast<const uint4 *>(P.vendor_first);
+    for (uint32_t i = gtid; i < 65536u / 2u; i += gthreads) {
+        const uint4 x = src[i];
+        for (int q = 0; q < P.tg.n; q++) reinterpret_cast<uint4 *>(P.tg.region[q] + P.o_a)[i] = x;
     }
-    if (P.clear_next && gtid < (uint32_t)(A_WORDS - 65536)) nx[65536 + gtid] = KX_NO_OFF;
 }
 __device__ __forceinline__ void xa_finish(const XaParams &P) {
     const unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(P.trunc);
@@ -71,9 +98,8 @@ __device__ __forceinline__ void xa_finish(const XaParams &P) {
     if (c[KX_C_LONGLINE_HINT] && !P.have_trunc) st |= XS_NEED_TRUNC;
     for (int q = 0; q < P.tg.n; q++) {
         unsigned long long *a = reinterpret_cast<unsigned long long *>(P.tg.region[q] + P.o_a);
-        if (t != KX_NO_OFF) atomicMin(a + A_TRUNC, t);
-        for (int k = 0; k < XS_BITS; k++)
-            if ((st >> k) & 1u) atomicMin(a + A_STATUS0 + k, 0ull);
+        a[A_TRUNC] = t;
+        a[A_STATUS] = st;
     }
     __threadfence_system();
     if (P.raise_flags)

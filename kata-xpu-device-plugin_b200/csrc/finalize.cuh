@@ -105,10 +105,9 @@ struct FinalizeParams {
     const uint8_t *text;  // shard text (local)
     unsigned long long n, base;
     KxTableDev tab;
-    // validity is judged against these (single text: the table's own; sharded load: the
-    // all-reduced minima of every rank, comm.cu)
-    const unsigned long long *vendor_first;
-    const unsigned long long *trunc;
+    // validity is judged against the first anchors / cut-off of the WHOLE text: the table's own
+    // (single text) or the minimum over every rank's phase-A block (sharded load, comm.cu)
+    kxx::MinView mv;
     uint32_t *row_key;
     unsigned long long *row_line;
     unsigned long long *row_anchor;
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const
     }
     const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5, sub = lane & 7u, grp = lane >> 3;
     const uint32_t nslots = F.tab.cap + 1u;
-    const unsigned long long trunc = *F.trunc;
+    const unsigned long long trunc = kxx::min_view_trunc(F.mv);
     // the CTA's warps step together: row handles and blob space are claimed once per CTA and step
     // (same-address atomics run at ~1 per ns: one pair per warp and step was the whole kernel time)
     for (uint32_t c0 = blockIdx.x * SF_WARPS * (uint32_t)SF_BATCH; c0 < nslots; c0 += gridDim.x * SF_WARPS * (uint32_t)SF_BATCH) {
@@ -173,7 +172,7 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const
             valid = line != KX_NO_OFF && !(slot < F.tab.cap && key == KX_EMPTY_KEY);
             if (valid) {
                 anchor = F.tab.slots[slot].min_anchor;
-                valid = anchor == F.vendor_first[key >> 16] && line < trunc;
+                valid = anchor == kxx::min_view_first(F.mv, key >> 16) && line < trunc;
             }
         }
         const uint32_t vm = __ballot_sync(0xffffffffu, valid);

@@ -42,7 +42,6 @@ struct KxXaHook {
 int32_t kx_launch_parse(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base,
                         unsigned long long carry_in, const KxXaHook *xa);
 int32_t kx_launch_trunc(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base);
-// validity + names; vendor_first / trunc: what validity is judged against (nullptr: the table's own)
 // slab (may be null): sharded load -- rows and names go into this rank's slab instead of the table's arrays
 struct KxSlabOut {
     uint8_t *rows;
@@ -50,9 +49,9 @@ struct KxSlabOut {
     uint8_t *blob;
     uint32_t blob_cap;
 };
+// mv (may be null: the table's own minima): what validity is judged against
 int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base,
-                           const unsigned long long *vendor_first, const unsigned long long *trunc, const kxx::WaitSpec *wait,
-                           const KxSlabOut *slab);
+                           const kxx::MinView *mv, const kxx::WaitSpec *wait, const KxSlabOut *slab);
 int32_t kx_launch_lookup(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *d_keys, size_t n, int32_t *d_rows);
 // growth policy shared by the single and the sharded load; returns false when the limit is reached
 bool kx_grow_cap(uint32_t *cap, bool table_full);
