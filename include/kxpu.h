@@ -136,6 +136,13 @@ int32_t kxpu_lookup_device(kxpu_ctx *ctx, kxpu_table *t, const uint32_t *d_keys,
 int32_t kxpu_pciids_join_device(kxpu_ctx *ctx, const void *d_text, size_t n, const uint32_t *d_keys,
                                 size_t nq, int32_t *d_rows_out, kxpu_table **out);
 
+/* The same from host buffers: text and keys are copied to the GPU, the row handles come back in
+ * rows_out, ONE host round trip.  This is the start-up path of the plugin: createDevicePlugins needs
+ * the name of every device id once (device_plugin.go:91-105).  A small text (the real pci.ids is
+ * 1.4 MB) is parsed, folded, finalized and joined by one cooperative kernel launch. */
+int32_t kxpu_pciids_join(kxpu_ctx *ctx, const uint8_t *text, size_t n, const uint32_t *keys, size_t nq,
+                         int32_t *rows_out, kxpu_table **out);
+
 /* Sanitised resource names for row handles (device_plugin.go:241-251: TrimPrefix,
  * TrimSpace, ToUpper, '/'->'_', '.'->'_', \s+ -> '_', strip [^a-zA-Z0-9_.]).
  * Name i occupies out[offsets[i] .. offsets[i+1]); a miss row yields an empty name

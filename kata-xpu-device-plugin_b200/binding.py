@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "kxpu_last_timings", "kxpu_set_stage_timing", "kxpu_timer_begin", "kxpu_timer_end", "kxpu_dev_alloc", "kxpu_dev_free", "kxpu_dev_upload", "kxpu_dev_download",
     "kxpu_dev_replicate", "kxpu_pinned_alloc", "kxpu_pinned_free", "kxpu_sync", "kxpu_pciids_load",
     "kxpu_pciids_load_device", "kxpu_table_free", "kxpu_table_rows", "kxpu_table_export", "kxpu_lookup",
-    "kxpu_lookup_device", "kxpu_pciids_join_device", "kxpu_names", "kxpu_comm_unique_id", "kxpu_comm_init", "kxpu_comm_destroy",
+    "kxpu_lookup_device", "kxpu_pciids_join_device", "kxpu_pciids_join", "kxpu_names", "kxpu_comm_unique_id", "kxpu_comm_init", "kxpu_comm_destroy",
     "kxpu_pciids_load_sharded", "kxpu_pciids_join_sharded", "kxpu_plan_shards", "kxpu_ctx_create_multi", "kxpu_multi_destroy",
     "kxpu_multi_size", "kxpu_multi_ctx", "kxpu_multi_pciids_join", "kxpu_classify", "kxpu_cdi_emit", "kxpu_alloc_names",
     "kxpu_lw_encode",
@@ -101,6 +101,7 @@ def load_library():
         "kxpu_lookup": (i32, [vp, vp, vp, sz, vp]),
         "kxpu_lookup_device": (i32, [vp, vp, vp, sz, vp]),
         "kxpu_pciids_join_device": (i32, [vp, vp, sz, vp, sz, vp, C.POINTER(vp)]),
+        "kxpu_pciids_join": (i32, [vp, vp, sz, vp, sz, vp, C.POINTER(vp)]),
         "kxpu_names": (i32, [vp, vp, vp, sz, vp, sz, vp, C.POINTER(sz)]),
         "kxpu_comm_unique_id": (i32, [vp]),
         "kxpu_comm_init": (i32, [vp, i32, i32, vp]),
@@ -240,6 +241,16 @@ class Kxpu:
         h = C.c_void_p()
         self._chk(self.L.kxpu_pciids_join_device(self.ctx, d_text, n, d_keys, nq, d_rows, C.byref(h)))
         return Table(self, h)
+
+    def pciids_join(self, text, keys):
+        """Host text + host keys -> (table, row handles): one call, one host round trip."""
+        a = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        rows = np.empty(len(keys), np.int32)
+        h = C.c_void_p()
+        self._chk(self.L.kxpu_pciids_join(self.ctx, a.ctypes.data if a.size else None, a.size, _ptr(keys), len(keys), _ptr(rows),
+                                          C.byref(h)))
+        return Table(self, h), rows
 
     def pciids_load_sharded(self, d_text, n, global_base):
         h = C.c_void_p()

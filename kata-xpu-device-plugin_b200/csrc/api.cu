@@ -9,6 +9,7 @@
 #include "internal.cuh"
 #include "pciids5.cu"
 #include "finalize.cuh"
+#include "small.cuh"
 #include "scan.cuh"
 
 void kx_exchange_destroy(kxpu_ctx *ctx);  // comm.cu
@@ -71,6 +72,7 @@ int32_t kx_ctx_create_on(int32_t ordinal, kxpu_ctx **out) {
                          (int)(sizeof(kxparse5::WarpSmem5) * kxparse::WARPS));
     const char *fr = getenv("KXPU_RCH");
     c->force_rch = (fr && fr[0] >= '1' && fr[0] <= '8' && !fr[1]) ? fr[0] - '0' : 0;
+    c->no_small = getenv("KXPU_NO_SMALL") != nullptr;
     *out = c;
     return KXPU_OK;
 }
@@ -461,7 +463,47 @@ struct KxJoin {  // optional batched join enqueued behind the finalize, in front
     const uint32_t *d_keys;
     size_t n;
     int32_t *d_rows;
+    int32_t *h_rows;  // optional: the row handles also go to this host buffer (inside the one round trip)
 };
+
+// chunks the cooperative small-text kernel can take: one per warp of a grid that is resident at once
+// (KXPU_NO_SMALL=1, read when the ctx is created, sends small texts through the big-text kernels: tests)
+static uint32_t small_text_chunks(kxpu_ctx *ctx) {
+    if (ctx->small_chunks < 0) {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        cudaFuncSetAttribute(kxsmall::small_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kxparse::WARPS * kxparse::STG_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kxsmall::small_load_kernel, kxparse::NT, kxparse::WARPS * kxparse::STG_BYTES);
+        cudaGetLastError();
+        ctx->small_chunks = (coop && !ctx->no_small) ? per_sm * ctx->sm_count * kxparse::WARPS : 0;
+    }
+    return (uint32_t)ctx->small_chunks;
+}
+
+// the whole load (+ join) of a small text as one cooperative launch (small.cuh)
+static int32_t launch_small(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, const KxJoin *join) {
+    using namespace kxparse;
+    kxsmall::SmallParams P;
+    memset(&P, 0, sizeof P);
+    P.text = d_text; P.n = n;
+    P.num_chunks = (uint32_t)((n + CW - 1) / CW);
+    P.tma_limit = n >= (size_t)STG_BYTES ? (uint32_t)((n - STG_BYTES) / CW) + 1u : 0u;
+    P.state = t->range_words;
+    FinalizeParams &F = P.F;
+    F.text = d_text; F.n = n; F.base = 0; F.tab = t->dev;
+    F.mv.a = t->dev.vendor_first; F.mv.stride = 0; F.mv.n = 1; F.mv.trunc1 = t->dev.trunc;
+    F.row_key = t->row_key; F.row_line = t->row_line; F.row_anchor = t->row_anchor;
+    F.row_name_off = t->row_name_off; F.row_name_len = t->row_name_len;
+    F.blob = t->blob; F.blob_cap = t->blob_cap;
+    if (join) { P.keys = join->d_keys; P.nq = join->n; P.rows_out = join->d_rows; }
+    void *args[] = {&P};
+    // the whole resident grid: phases 1 / 2 use one warp per chunk, the names and the join every warp
+    const unsigned grid = std::max<unsigned>((P.num_chunks + WARPS - 1) / WARPS, (unsigned)(ctx->small_chunks / WARPS));
+    KxTimer tm(ctx, KXPU_T_PARSE);
+    KX_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kxsmall::small_load_kernel, dim3(grid), dim3(NT), args, (size_t)WARPS * STG_BYTES, ctx->stream));
+    KX_LAUNCHED(ctx);
+    return KXPU_OK;
+}
 
 // Parse d_text[0..n), finalize, optionally join; ONE host round trip at the end (counters).
 static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t n, kxpu_table **out, const KxJoin *join) {
@@ -479,15 +521,21 @@ static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t 
         kxpu_table *t = nullptr;
         int32_t rc = kx_table_acquire(ctx, cap, blob_cap, num_chunks, &t);
         if (rc != KXPU_OK) return rc;
-        rc = kx_launch_parse(ctx, t, d_text, n, 0, 0, nullptr);
-        // a text with a >= 2 KiB stretch without a newline was seen on an earlier attempt: the exact
-        // bufio.ErrTooLong cut-off is computed before the finalize
-        if (rc == KXPU_OK && have_trunc) rc = kx_launch_trunc(ctx, t, d_text, n, 0);
-        if (rc == KXPU_OK) rc = kx_launch_finalize(ctx, t, d_text, n, 0, nullptr, nullptr, nullptr);
-        // the join does not need anything from the host: enqueue it before the round trip below
-        // (it is simply run again if the table has to be rebuilt)
-        if (rc == KXPU_OK && join) rc = kx_launch_lookup(ctx, t, join->d_keys, join->n, join->d_rows);
+        if (num_chunks > 0 && num_chunks <= small_text_chunks(ctx) && !have_trunc) {
+            // a small text (the real pci.ids): parse, fold, names and join in ONE cooperative launch
+            rc = launch_small(ctx, t, d_text, n, join);
+        } else {
+            rc = kx_launch_parse(ctx, t, d_text, n, 0, 0, nullptr);
+            // a text with a >= 2 KiB stretch without a newline was seen on an earlier attempt: the exact
+            // bufio.ErrTooLong cut-off is computed before the finalize
+            if (rc == KXPU_OK && have_trunc) rc = kx_launch_trunc(ctx, t, d_text, n, 0);
+            if (rc == KXPU_OK) rc = kx_launch_finalize(ctx, t, d_text, n, 0, nullptr, nullptr, nullptr);
+            // the join does not need anything from the host: enqueue it before the round trip below
+            // (it is simply run again if the table has to be rebuilt)
+            if (rc == KXPU_OK && join) rc = kx_launch_lookup(ctx, t, join->d_keys, join->n, join->d_rows);
+        }
         if (rc != KXPU_OK) { kx_table_release(ctx, t); return rc; }
+        if (join && join->h_rows && join->n) cudaMemcpyAsync(join->h_rows, join->d_rows, join->n * 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
@@ -533,7 +581,7 @@ extern "C" int32_t kxpu_pciids_join_device(kxpu_ctx *ctx, const void *d_text, si
     KX_ENTER(ctx);
     if (!out || (!d_text && n) || (nq && (!d_keys || !d_rows_out))) return KXPU_E_INVALID;
     kx_clear_timings(ctx);
-    const KxJoin j{d_keys, nq, d_rows_out};
+    const KxJoin j{d_keys, nq, d_rows_out, nullptr};
     return kx_build_table_join(ctx, (const uint8_t *)d_text, n, out, &j);
 }
 
@@ -569,6 +617,26 @@ extern "C" int32_t kxpu_pciids_load(kxpu_ctx *ctx, const uint8_t *text, size_t n
         return KXPU_E_CUDA;
     }
     return kx_build_table_join(ctx, (const uint8_t *)ctx->d_stage, n, out, nullptr);
+}
+
+extern "C" int32_t kxpu_pciids_join(kxpu_ctx *ctx, const uint8_t *text, size_t n, const uint32_t *keys, size_t nq, int32_t *rows_out,
+                                    kxpu_table **out) {
+    KX_ENTER(ctx);
+    if (!out || (!text && n) || (nq && (!keys || !rows_out))) return KXPU_E_INVALID;
+    kx_clear_timings(ctx);
+    // staging: [text | pad to 16 | keys | rows]
+    const size_t o_keys = align_up(n + 16, 256), o_rows = o_keys + align_up(nq * 4 + 16, 256);
+    int32_t rc = stage_reserve(ctx, o_rows + nq * 4 + 16);
+    if (rc != KXPU_OK) return rc;
+    uint8_t *d = (uint8_t *)ctx->d_stage;
+    cudaError_t e = cudaMemcpyAsync(d, text, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nq) e = cudaMemcpyAsync(d + o_keys, keys, nq * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        KX_SET_ERR(ctx, "H2D copy of the text / keys failed: %s", cudaGetErrorString(e));
+        return KXPU_E_CUDA;
+    }
+    const KxJoin j{(const uint32_t *)(d + o_keys), nq, (int32_t *)(d + o_rows), rows_out};
+    return kx_build_table_join(ctx, d, n, out, &j);
 }
 
 extern "C" int32_t kxpu_table_free(kxpu_ctx *ctx, kxpu_table *t) {

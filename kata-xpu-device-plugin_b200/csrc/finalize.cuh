@@ -145,11 +145,10 @@ __device__ __forceinline__ void finalize_store_row(const FinalizeParams &F, uint
 // path.  KX_C_NEED_TRUNC: 0 = cut-off never computed, 1 = computed (trunc_kernel), 2 = asked for:
 // when the parse raised the long-line hint and the cut-off is not there yet, every block leaves
 // (the test does not depend on what block 0 writes) and the host finalizes again.
-__global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const FinalizeParams F) {
+__device__ __forceinline__ void select_finalize_body(const FinalizeParams &F) {
     __shared__ __align__(16) uint8_t s_raw[SF_WARPS][4][SF_WIN + 16];
     __shared__ uint8_t s_name[SF_WARPS][SF_BATCH][SF_WIN];
     __shared__ uint32_t s_cnt[SF_WARPS], s_bytes[SF_WARPS], s_row0, s_blob0;
-    kxx::wait_flags_cta(F.wait);
     if (F.tab.counters[KX_C_LONGLINE_HINT] != 0u && F.tab.counters[KX_C_NEED_TRUNC] != 1u) {
         if (blockIdx.x == 0 && threadIdx.x == 0) F.tab.counters[KX_C_NEED_TRUNC] = 2u;
         return;
@@ -389,6 +388,11 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const
         }
         __syncthreads();  // the staging rows and the claim words are reused by the next step
     }
+}
+
+__global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const FinalizeParams F) {
+    kxx::wait_flags_cta(F.wait);
+    select_finalize_body(F);
 }
 
 // ------------------------------------------------------------------------------

@@ -32,6 +32,7 @@
 #define KX_C_BLOB_CURSOR 5
 #define KX_C_BLOB_OVERFLOW 6
 #define KX_C_NEED_TRUNC 7
+#define KX_C_GRIDBAR 8   // small-text kernel: grid barrier arrivals
 #define KX_C_NSEL 9
 #define KX_C_DEFER 10
 #define KX_C_XSTATUS 11   // sharded load: KX_XS_* bits, identical on every rank after the exchange

@@ -111,7 +111,9 @@ def classify(recs):
     bus = 0
     for r in recs:
         accept.append(None)
-        if r.get("is_dir") or r.get("vendor") is None:
+        # an id file shorter than 2 bytes makes the reference panic (data[2:], device_plugin.go:189); the
+        # documented behaviour here is "skipped like a read error" (domain restrictions)
+        if r.get("is_dir") or r.get("vendor") is None or len(r["vendor"]) < 2:
             continue
         vendor = r["vendor"][2:].strip(b"\n")
         if vendor != b"10de":
@@ -122,7 +124,7 @@ def classify(recs):
             continue
         g = r["group"]
         if g not in iommu:
-            if r.get("device") is None:
+            if r.get("device") is None or len(r["device"]) < 2:
                 continue
             dev = r["device"][2:].strip(b"\n")
             devmap.setdefault(dev, []).append(g)

@@ -383,3 +383,46 @@ def test_name_lengths_around_the_finalize_windows(kx, oracle):
             assert nm == (oracle.device_name(text, k)[1] or b""), hex(k)
     finally:
         tab.free()
+
+
+def test_host_join_one_round_trip(kx, oracle, pci_text, oracle_rows, workloads):
+    """kxpu_pciids_join (host text + host keys, one call): same table and row handles as load + lookup,
+    on the small-text kernel (pci.ids) and on a text that is too large for it."""
+    for text in (pci_text, pci_text * 8):
+        q = workloads.make_queries(oracle_rows["key"], 3000, 5)
+        tab, rows = kx.pciids_join(text, q)
+        keys, offs, tr = kx.table_export(tab)
+        want = oracle.table_build(text)
+        assert np.array_equal(keys, want["key"]) and np.array_equal(offs, want["line_off"])
+        line_of_row = np.full(tab.rows + 1, -1, np.int64)
+        line_of_row[tr] = offs.astype(np.int64)
+        got = np.where(rows >= 0, line_of_row[np.maximum(rows, 0)], -1)
+        order = np.argsort(want["key"])
+        sk = want["key"][order]
+        pos = np.searchsorted(sk, q)
+        pos[pos >= len(sk)] = 0
+        exp = np.where(sk[pos] == q, want["line_off"][order][pos].astype(np.int64), -1)
+        assert np.array_equal(got, exp)
+        assert np.array_equal(rows, kx.lookup(tab, q))
+        tab.free()
+    tab, rows = kx.pciids_join(b"", np.array([1, 2], np.uint32))
+    assert tab.rows == 0 and (rows == -1).all()
+    tab.free()
+
+
+def test_small_texts_through_the_big_text_kernels(oracle, pci_text, monkeypatch):
+    """Small texts normally take the cooperative one-launch kernel; KXPU_NO_SMALL=1 sends them through
+    parse_kernel_v5 + resolve + select_finalize, which must agree (ragged sizes, edge texts, real file)."""
+    import kxpu_b200 as K
+    monkeypatch.setenv("KXPU_NO_SMALL", "1")
+    k = K.Kxpu(0)
+    try:
+        check_text(k, oracle, pci_text)
+        for text in EDGE_TEXTS:
+            check_text(k, oracle, text)
+        for n in (1, 5, 2047, 2048, 2049, 4096, 300001):
+            check_text(k, oracle, pci_text[:n])
+        rng = np.random.default_rng(8)
+        check_text(k, oracle, _big_random_text(rng, 6000, 80, 0.4), extra_keys=[0x00010001, 0x00630000])
+    finally:
+        k.close()
