@@ -151,6 +151,29 @@ int32_t kxpu_pciids_join(kxpu_ctx *ctx, const uint8_t *text, size_t n, const uin
 int32_t kxpu_names(kxpu_ctx *ctx, kxpu_table *t, const int32_t *rows, size_t n,
                    uint8_t *out, size_t cap, uint32_t *offsets, size_t *need);
 
+/* ------------------------------- the rest of the pci.ids model */
+
+/* Subsystem rows and the class / subclass / prog-if section of the same text, on top of a finished
+ * (vendor,device) table.  The reference scans these lines and ignores them
+ * (device_plugin.go:229-237); their meaning is the file's own format statement
+ * (utils/pci.ids:23-27, :38195-38200), taken with the reference's matching rules one level down:
+ * raw byte prefixes, the FIRST line wins at every level (vendor / class line, device / subclass line
+ * inside it, subsystem / prog-if line inside that), bufio line semantics.
+ *   kind 0  vendor     key = vendor
+ *   kind 1  subsystem  key = vendor<<48 | device<<32 | subvendor<<16 | subdevice
+ *   kind 2  class section: class 1<<24 | c<<16;  subclass 2<<24 | c<<16 | s<<8;  prog-if 3<<24 | c<<16 | s<<8 | p
+ * A row is (key, offset of its line in the text); names are the rest of that line.
+ * d_text / n / t: the text the table `t` was built from (device memory, still resident); `t` must
+ * outlive the returned object. */
+typedef struct kxpu_full kxpu_full;
+int32_t kxpu_pciids_full_load_device(kxpu_ctx *ctx, const void *d_text, size_t n, kxpu_table *t, kxpu_full **out);
+int32_t kxpu_full_free(kxpu_ctx *ctx, kxpu_full *f);
+/* rows of one kind in file order; on KXPU_E_NOSPACE *n_rows holds the required count */
+int32_t kxpu_full_export(kxpu_ctx *ctx, kxpu_full *f, int32_t kind, uint64_t *keys, uint64_t *line_off, size_t cap,
+                         uint32_t *n_rows);
+/* batched probe (host buffers): line_off_out[i] = offset of the line of keys[i], or -1 */
+int32_t kxpu_full_lookup(kxpu_ctx *ctx, kxpu_full *f, int32_t kind, const uint64_t *keys, size_t n, int64_t *line_off_out);
+
 /* ------------------------------------------------------------- multi-GPU */
 
 /* The pci.ids text shards by vendor-id range: a cut may only fall where a

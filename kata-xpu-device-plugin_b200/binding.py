@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "kxpu_lookup_device", "kxpu_pciids_join_device", "kxpu_pciids_join", "kxpu_names", "kxpu_comm_unique_id", "kxpu_comm_init", "kxpu_comm_destroy",
     "kxpu_pciids_load_sharded", "kxpu_pciids_join_sharded", "kxpu_plan_shards", "kxpu_ctx_create_multi", "kxpu_multi_destroy",
     "kxpu_multi_size", "kxpu_multi_ctx", "kxpu_multi_pciids_join", "kxpu_classify", "kxpu_cdi_emit", "kxpu_alloc_names",
-    "kxpu_lw_encode",
+    "kxpu_lw_encode", "kxpu_pciids_full_load_device", "kxpu_full_free", "kxpu_full_export", "kxpu_full_lookup",
 ]
 
 
@@ -118,6 +118,10 @@ def load_library():
         "kxpu_cdi_emit": (i32, [vp, i32, vp, sz, vp, sz, C.POINTER(sz)]),
         "kxpu_alloc_names": (i32, [vp, vp, sz, vp, sz, vp, C.POINTER(sz)]),
         "kxpu_lw_encode": (i32, [vp, vp, vp, sz, vp, sz, C.POINTER(sz)]),
+        "kxpu_pciids_full_load_device": (i32, [vp, vp, sz, vp, C.POINTER(vp)]),
+        "kxpu_full_free": (i32, [vp, vp]),
+        "kxpu_full_export": (i32, [vp, vp, i32, vp, vp, sz, C.POINTER(C.c_uint32)]),
+        "kxpu_full_lookup": (i32, [vp, vp, i32, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -291,6 +295,30 @@ class Kxpu:
                                     C.byref(need)))
         blob = out[:need.value].tobytes()
         return [blob[offs[i]:offs[i + 1]] for i in range(len(rows))], blob, offs
+
+    # -- the rest of the pci.ids model
+    def full_load_device(self, d_text, n, table):
+        h = C.c_void_p()
+        self._chk(self.L.kxpu_pciids_full_load_device(self.ctx, d_text, n, table.handle, C.byref(h)))
+        return h
+
+    def full_free(self, full):
+        self._chk(self.L.kxpu_full_free(self.ctx, full))
+
+    def full_export(self, full, kind):
+        n = C.c_uint32(0)
+        rc = self.L.kxpu_full_export(self.ctx, full, kind, None, None, 0, C.byref(n))
+        if rc not in (KXPU_OK, E_NOSPACE):
+            self._chk(rc)
+        keys, offs = np.empty(n.value, np.uint64), np.empty(n.value, np.uint64)
+        self._chk(self.L.kxpu_full_export(self.ctx, full, kind, _ptr(keys), _ptr(offs), n.value, C.byref(n)))
+        return keys, offs
+
+    def full_lookup(self, full, kind, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.empty(len(keys), np.int64)
+        self._chk(self.L.kxpu_full_lookup(self.ctx, full, kind, _ptr(keys), len(keys), _ptr(out)))
+        return out
 
     # -- multi GPU
     def comm_unique_id(self):

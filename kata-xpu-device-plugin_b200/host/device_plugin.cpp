@@ -4,7 +4,9 @@
 
 #include <dirent.h>
 #include <poll.h>
+#include <linux/netlink.h>
 #include <sys/inotify.h>
+#include <sys/socket.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -66,6 +68,63 @@ Plugin::Plugin(kxpu_ctx *ctx) : ctx_(ctx) {
     readLink = readLinkFunc;
     readIDFromFile = readIDFromFileFunc;
     returnIommuMap = [this]() -> const OrderedMap<std::vector<NvidiaGpuDevice>> & { return iommuMap; };
+    bindGeneration = [this](uint64_t &generation) {
+        if (!bindWatcher_.healthy() && bindWatcher_.start()) return false;
+        generation = bindWatcher_.generation();
+        return bindWatcher_.healthy();
+    };
+}
+
+// ---------------------------------------------------------------------------- bind / unbind uevents
+BindWatcher::~BindWatcher() {
+    if (fd_ >= 0) close(fd_);
+}
+
+Error BindWatcher::start() {
+    if (fd_ >= 0) close(fd_);
+    lost_ = false;
+    fd_ = socket(AF_NETLINK, SOCK_DGRAM | SOCK_CLOEXEC | SOCK_NONBLOCK, NETLINK_KOBJECT_UEVENT);
+    if (fd_ < 0) return fail(std::string("uevent socket: ") + strerror(errno));
+    struct sockaddr_nl sa;
+    memset(&sa, 0, sizeof sa);
+    sa.nl_family = AF_NETLINK;
+    sa.nl_groups = 1;  // kernel uevent multicast group
+    if (bind(fd_, (struct sockaddr *)&sa, sizeof sa) != 0) {
+        Error e = fail(std::string("uevent bind: ") + strerror(errno));
+        close(fd_);
+        fd_ = -1;
+        return e;
+    }
+    return Error();
+}
+
+// "ACTION@DEVPATH\0KEY=VALUE\0..." -- a pci function changing its driver or coming / going
+void BindWatcher::feed(const char *msg, size_t len) {
+    const char *end = msg + len;
+    std::string action, subsystem;
+    for (const char *p = msg; p < end; p += strlen(p) + 1) {
+        if (strncmp(p, "ACTION=", 7) == 0) action = p + 7;
+        else if (strncmp(p, "SUBSYSTEM=", 10) == 0) subsystem = p + 10;
+        if (memchr(p, 0, (size_t)(end - p)) == nullptr) break;  // unterminated tail
+    }
+    if (subsystem == "pci" && (action == "bind" || action == "unbind" || action == "add" || action == "remove")) gen_++;
+}
+
+uint64_t BindWatcher::generation() {
+    if (fd_ < 0) return gen_;
+    char buf[8192];
+    for (;;) {
+        ssize_t k = recv(fd_, buf, sizeof buf - 1, 0);
+        if (k > 0) {
+            buf[k] = 0;
+            feed(buf, (size_t)k);
+            continue;
+        }
+        if (k < 0 && errno == EINTR) continue;
+        if (k < 0 && errno == ENOBUFS) { lost_ = true; gen_ += 1ull << 32; }  // messages were dropped
+        break;
+    }
+    return gen_;
 }
 
 Plugin::~Plugin() {
@@ -309,6 +368,8 @@ static std::string devIdString(uint64_t packed) {
 Error Plugin::createIommuDeviceMap() {
     iommuMap.clear();   // :127
     deviceMap.clear();  // :128
+    // the generation is read BEFORE the walk: an event during the walk makes the snapshot stale, never fresh
+    haveSnapshotGen_ = snapshotValidation && bindGeneration && bindGeneration(snapshotGen_);
     std::vector<kxpu_devrec> recs;
     Error e = gatherRecordsFast(recs);  // same records as gatherRecords (falls back to it when a seam was replaced)
     if (e) { fprintf(stderr, "%s\n", e.message.c_str()); }  // Walk's error is ignored by the reference (:132)
@@ -469,11 +530,25 @@ Error Plugin::InitiateDevicePlugin() {
 Error Plugin::Allocate(const std::vector<std::string> &devicesIDs, ContainerAllocateResponse &resp) {
     std::vector<uint64_t> devIndexes;
     const auto &returnedMap = returnIommuMap();
+    // snapshot validation (off by default): every device of returnedMap was NVIDIA, bound to vfio-pci and in
+    // this group when it was discovered; if no pci function was bound / unbound / added / removed since, the
+    // live reads below would return exactly that
+    bool fromSnapshot = false;
+    if (snapshotValidation && haveSnapshotGen_ && bindGeneration) {
+        uint64_t now = 0;
+        fromSnapshot = bindGeneration(now) && now == snapshotGen_;
+    }
     for (const std::string &iommuId : devicesIDs) {  // :324
         const std::vector<NvidiaGpuDevice> *nvDevs = nullptr;
         for (const auto &kv : returnedMap) if (kv.first == iommuId) { nvDevs = &kv.second; break; }
         if (!nvDevs) continue;  // unknown group id: empty nvDevs, no error (:327)
         for (const NvidiaGpuDevice &dev : *nvDevs) {
+            if (fromSnapshot) {
+                snapshotValidations++;
+                devIndexes.push_back(dev.index);  // :340
+                continue;
+            }
+            liveValidations++;
             std::string iommuGroup, vendor;
             if (!readLink(basePath, dev.addr, "iommu_group", iommuGroup) || iommuGroup != iommuId)  // :329-333
                 return fail("invalid allocation request: unknown device: " + dev.addr);
@@ -713,6 +788,31 @@ int kxh_allocate(void *h, const char *ids_csv, char *json, size_t cap) {
     for (size_t i = 0; i < resp.CDIDevices.size(); i++) { if (i) o += ','; jstr(o, resp.CDIDevices[i]); }
     o += "]}";
     return copy_out(o, json, cap);
+}
+
+// ---- snapshot validation of Allocate: tests drive the generation through the seam
+void kxh_snapshot_enable(void *h, const uint64_t *generation, const int *healthy) {
+    Plugin *p = (Plugin *)h;
+    p->snapshotValidation = true;
+    if (generation) p->bindGeneration = [generation, healthy](uint64_t &g) { g = *generation; return !healthy || *healthy != 0; };
+}
+void kxh_validation_counts(void *h, uint64_t *live, uint64_t *snapshot) {
+    Plugin *p = (Plugin *)h;
+    *live = p->liveValidations;
+    *snapshot = p->snapshotValidations;
+}
+// BindWatcher's uevent parser, message by message (CPU tests): returns the generation after the message
+uint64_t kxh_uevent_feed(void **w, const char *msg, size_t len) {
+    if (!*w) *w = new device_plugin::BindWatcher();
+    device_plugin::BindWatcher *bw = (device_plugin::BindWatcher *)*w;
+    if (msg) bw->feed(msg, len);
+    return bw->generation();
+}
+void kxh_uevent_free(void *w) { delete (device_plugin::BindWatcher *)w; }
+// the real socket: 0 = opened (and healthy), < 0 = this box does not allow it
+int kxh_uevent_socket_ok() {
+    device_plugin::BindWatcher bw;
+    return bw.start() ? -1 : (bw.healthy() ? 0 : -2);
 }
 
 // ---- health watcher (tests): a plugin can be added by hand so that no GPU is needed for the host logic

@@ -87,6 +87,33 @@ class HealthWatcher {
     int setHealth(const std::string &id, const char *health);
 };
 
+// SURVEY 8(f) row 2, second half: what makes a snapshot of the discovery trustworthy.  Allocate
+// re-validates every device against sysfs (readlink iommu_group + read vendor, two syscalls per device,
+// generic_device_plugin.go:329-338) because a device may have been re-bound since discovery.  The kernel
+// announces exactly that: bind / unbind / add / remove uevents of the pci subsystem on the
+// NETLINK_KOBJECT_UEVENT socket (bind / unbind since Linux 4.14).  BindWatcher counts them: while the
+// generation it reports equals the one recorded at discovery, no PCI function changed its driver and the
+// snapshot answers what the live reads would answer.
+class BindWatcher {
+  public:
+    BindWatcher() = default;
+    ~BindWatcher();
+    BindWatcher(const BindWatcher &) = delete;
+    BindWatcher &operator=(const BindWatcher &) = delete;
+    Error start();            // opens the uevent socket (needs no privilege beyond a netlink socket)
+    bool healthy() const { return fd_ >= 0 && !lost_; }
+    // drains the socket; the generation grows by one per pci bind / unbind / add / remove event and jumps
+    // when the kernel reports lost messages (ENOBUFS): then nothing can be said about what was missed
+    uint64_t generation();
+    // feeds one raw uevent message (tests; also what generation() calls per datagram)
+    void feed(const char *msg, size_t len);
+
+  private:
+    int fd_ = -1;
+    bool lost_ = false;
+    uint64_t gen_ = 0;
+};
+
 class Plugin {
   public:
     // ---- seams (device_plugin.go:36-39, generic_device_plugin.go:34)
@@ -96,6 +123,14 @@ class Plugin {
     std::function<bool(const std::string &base, const std::string &addr, const std::string &link, std::string &out)> readLink;
     std::function<bool(const std::string &base, const std::string &addr, const std::string &prop, std::string &out)> readIDFromFile;
     std::function<const OrderedMap<std::vector<NvidiaGpuDevice>> &()> returnIommuMap;
+    // Allocate re-validation (generic_device_plugin.go:329-338).  false (default) = the reference's live
+    // reads for every device of every request.  true = answer from the discovery snapshot as long as
+    // bindGeneration() still returns the value recorded by createIommuDeviceMap; any change (or an
+    // unhealthy watcher) falls back to the live reads for that request.  bindGeneration is a seam: by
+    // default it asks the BindWatcher (started on first use), tests replace it.
+    bool snapshotValidation = false;
+    std::function<bool(uint64_t &generation)> bindGeneration;
+    uint64_t liveValidations = 0, snapshotValidations = 0;  // devices validated either way (tests, metrics)
 
     // ---- state (device_plugin.go:31,34)
     OrderedMap<std::vector<NvidiaGpuDevice>> iommuMap;  // group id -> devices
@@ -133,6 +168,9 @@ class Plugin {
     kxpu_ctx *ctx_;
     kxpu_table *table_ = nullptr;
     Error ensureTable();
+    BindWatcher bindWatcher_;
+    bool haveSnapshotGen_ = false;
+    uint64_t snapshotGen_ = 0;
 };
 
 }  // namespace device_plugin

@@ -655,3 +655,96 @@ double kxo_bench_parse_mt(const uint8_t *text, size_t n, int threads, const uint
     if (parse_s) *parse_s = t1 - t0;
     return t2 - t0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* the rest of the pci.ids model.  The reference scans the   */
+/* subsystem lines and the class section and ignores them (device_plugin.go:    */
+/* 229-237); what they MEAN is stated by the file itself (utils/pci.ids:23-27,  */
+/* :38195-38200):                                                               */
+/*     vendor  vendor_name                                                      */
+/*     \t device  device_name                                                   */
+/*     \t\t subvendor subdevice  subsystem_name                                 */
+/*     C class  class_name / \t subclass  name / \t\t prog-if  name             */
+/* Restated with the reference's own matching rules carried one level down:     */
+/* raw byte prefixes, first occurrence wins at every level, a block ends at the */
+/* first line that is neither a comment nor indented, bufio line semantics.     */
+/* Rows (key, offset of the line) in file order:                                */
+/*   kind 0 vendor    key = v                                                   */
+/*   kind 1 subsystem key = v<<48 | d<<32 | sv<<16 | sd                         */
+/*   kind 2 class     key = 1<<24 | c<<16 ; subclass 2<<24 | c<<16 | s<<8 ;     */
+/*                    prog-if 3<<24 | c<<16 | s<<8 | p                          */
+/* ------------------------------------------------------------------------- */
+typedef struct kxo_row64 { uint64_t key; uint64_t line_off; } kxo_row64;
+
+static int parse_hex2(const uint8_t *s, size_t len, uint32_t *v) {
+    if (len < 2 || !is_lhex(s[0]) || !is_lhex(s[1])) return 0;
+    *v = (uint32_t)(hexval(s[0]) * 16 + hexval(s[1]));
+    return 1;
+}
+
+size_t kxo_full_build(const uint8_t *text, size_t n, int kind, kxo_row64 *rows, size_t cap) {
+    uint8_t *vendor_seen = (uint8_t *)calloc(65536, 1), *class_seen = (uint8_t *)calloc(256, 1);
+    uint8_t *dev_seen = (uint8_t *)calloc(65536 / 8, 1), *sub_seen = (uint8_t *)calloc(256 / 8, 1);
+    /* (subvendor, subdevice) / prog-if seen under the current device / subclass line: generation-stamped set */
+    size_t scap = 1u << 16;
+    uint64_t *skeys = (uint64_t *)calloc(scap, sizeof(uint64_t));
+    uint32_t *sgen = (uint32_t *)calloc(scap, sizeof(uint32_t)), gen = 0;
+    size_t pos = 0, ls, le, nrows = 0;
+    int vblock = 0, cblock = 0, dev_ok = 0, sub_ok = 0;
+    uint32_t cur_v = 0, cur_d = 0, cur_c = 0, cur_s = 0;
+#define KXO_EMIT(k) do { if (nrows < cap) { rows[nrows].key = (k); rows[nrows].line_off = ls; } nrows++; } while (0)
+    while (kxo_next_line(text, n, &pos, &ls, &le) == 1) {
+        size_t len = le - ls;
+        const uint8_t *l = text + ls;
+        if (len >= 1 && l[0] == '#') continue;
+        if (len >= 2 && l[0] == '\t' && l[1] == '\t') {
+            uint64_t key;
+            uint32_t a, b;
+            if (vblock && dev_ok && parse_hex4(l + 2, len - 2, &a) && len >= 11 && l[6] == ' ' && parse_hex4(l + 7, len - 7, &b))
+                key = ((uint64_t)cur_v << 48) | ((uint64_t)cur_d << 32) | ((uint64_t)a << 16) | b;
+            else if (cblock && sub_ok && parse_hex2(l + 2, len - 2, &a))
+                key = (3ull << 24) | ((uint64_t)cur_c << 16) | ((uint64_t)cur_s << 8) | a;
+            else
+                continue;
+            size_t h = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (scap - 1);
+            int dup = 0;
+            while (sgen[h] == gen) { if (skeys[h] == key) { dup = 1; break; } h = (h + 1) & (scap - 1); }
+            if (dup) continue;
+            sgen[h] = gen; skeys[h] = key;
+            if ((vblock && kind == 1) || (cblock && kind == 2)) KXO_EMIT(key);
+            continue;
+        }
+        if (len >= 1 && l[0] == '\t') {
+            uint32_t d;
+            dev_ok = sub_ok = 0;
+            gen++;  /* a new device / subclass line: its second-level set starts empty */
+            if (gen == 0) { memset(sgen, 0, scap * sizeof(uint32_t)); gen = 1; }
+            if (vblock && parse_hex4(l + 1, len - 1, &d)) {
+                if (!(dev_seen[d >> 3] & (1u << (d & 7)))) { dev_seen[d >> 3] |= (uint8_t)(1u << (d & 7)); dev_ok = 1; cur_d = d; }
+            } else if (cblock && parse_hex2(l + 1, len - 1, &d)) {
+                if (!(sub_seen[d >> 3] & (1u << (d & 7)))) {
+                    sub_seen[d >> 3] |= (uint8_t)(1u << (d & 7)); sub_ok = 1; cur_s = d;
+                    if (kind == 2) KXO_EMIT((2ull << 24) | ((uint64_t)cur_c << 16) | ((uint64_t)d << 8));
+                }
+            }
+            continue;
+        }
+        /* top-level line: ends any block; may start a vendor block or a class block */
+        vblock = cblock = dev_ok = sub_ok = 0;
+        uint32_t v;
+        if (len >= 4 && l[0] == 'C' && l[1] == ' ' && parse_hex2(l + 2, len - 2, &v)) {
+            if (!class_seen[v]) {
+                class_seen[v] = 1; cblock = 1; cur_c = v;
+                memset(sub_seen, 0, 256 / 8);
+                if (kind == 2) KXO_EMIT((1ull << 24) | ((uint64_t)v << 16));
+            }
+        } else if (parse_hex4(l, len, &v) && !vendor_seen[v]) {
+            vendor_seen[v] = 1; vblock = 1; cur_v = v;
+            memset(dev_seen, 0, 65536 / 8);
+            if (kind == 0) KXO_EMIT((uint64_t)v);
+        }
+    }
+#undef KXO_EMIT
+    free(vendor_seen); free(class_seen); free(dev_seen); free(sub_seen); free(skeys); free(sgen);
+    return nrows;
+}

@@ -238,3 +238,21 @@ def bench_parse_mt(text, keys, threads):
     ps = C.c_double(0)
     dt = lib().kxo_bench_parse_mt(p, n, threads, keys.ctypes.data, len(keys), offs.ctypes.data, C.byref(ps))
     return dt, ps.value, offs
+
+
+ROW64_DTYPE = np.dtype([("key", "<u8"), ("line_off", "<u8")])
+
+
+def full_build(text, kind):
+    """vendor (0) / subsystem (1) / class-section (2) rows (key, line_off) in file order."""
+    L = lib()
+    L.kxo_full_build.restype = C.c_size_t
+    L.kxo_full_build.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
+    p, n, keep = _buf(text)
+    cap = 1 << 15
+    rows = np.zeros(cap, dtype=ROW64_DTYPE)
+    nr = L.kxo_full_build(p, n, kind, rows.ctypes.data, cap)
+    if nr > cap:
+        rows = np.zeros(nr, dtype=ROW64_DTYPE)
+        nr = L.kxo_full_build(p, n, kind, rows.ctypes.data, nr)
+    return rows[:nr]

@@ -283,3 +283,70 @@ def test_fast_gather_error_behaviour_equals_walk(tmp_path):
     assert by_bdf[devs[201]["bdf"].encode()]["flags"] == 0 and by_bdf[devs[201]["bdf"].encode()]["driver"] == b""
     with pytest.raises(RuntimeError):
         fake_sysfs.gather_fast(str(tmp_path / "missing"), DEVREC_DTYPE)
+
+
+def test_bind_watcher_counts_pci_bind_events():
+    """BindWatcher (second half): the generation moves on pci bind / unbind / add / remove
+    uevents and on nothing else; the real NETLINK_KOBJECT_UEVENT socket opens where the box allows it."""
+    import ctypes as C
+    L = fake_sysfs.host_lib()
+    L.kxh_uevent_feed.restype = C.c_uint64
+    L.kxh_uevent_feed.argtypes = [C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    L.kxh_uevent_free.argtypes = [C.c_void_p]
+    w = C.c_void_p()
+
+    def feed(*fields):
+        m = b"\0".join(fields) + b"\0"
+        return L.kxh_uevent_feed(C.byref(w), m, len(m))
+    assert feed(b"add@/devices/virtual/net/x", b"ACTION=add", b"SUBSYSTEM=net") == 0
+    assert feed(b"bind@/devices/pci0000:00/0000:00:1f.0", b"ACTION=bind", b"DEVPATH=/devices/pci0000:00/0000:00:1f.0",
+                b"SUBSYSTEM=pci", b"DRIVER=vfio-pci") == 1
+    assert feed(b"unbind@/devices/x", b"ACTION=unbind", b"SUBSYSTEM=pci") == 2
+    assert feed(b"change@/devices/x", b"ACTION=change", b"SUBSYSTEM=pci") == 2
+    assert feed(b"remove@/devices/x", b"SUBSYSTEM=pci", b"ACTION=remove") == 3
+    assert feed(b"bind@/devices/x", b"ACTION=bind", b"SUBSYSTEM=usb") == 3
+    assert L.kxh_uevent_feed(C.byref(w), b"ACTION=bind\0SUBSYSTEM=pci", 26) == 4  # unterminated last field
+    L.kxh_uevent_free(w)
+    assert L.kxh_uevent_socket_ok() in (0, -1)  # sandboxes may forbid netlink sockets
+
+
+@pytest.mark.gpu
+def test_allocate_snapshot_validation_follows_the_generation(tmp_path, kx, pci_text):
+    """snapshotValidation (default off): while the bind generation equals the one recorded at discovery Allocate
+    answers from the snapshot -- no sysfs reads --, any change (or an unhealthy watcher) falls back to the
+    reference's live reads, which then see the re-bound device (generic_device_plugin.go:329-338)."""
+    import ctypes as C
+    base = fake_sysfs.make_tree(str(tmp_path), DEVICES)
+    pciids = tmp_path / "pci.ids"
+    pciids.write_bytes(pci_text)
+    cdi = tmp_path / "cdi"
+    cdi.mkdir()
+    hp = fake_sysfs.HostPlugin(kx, base, str(pciids), str(cdi) + "/")
+    gen, healthy = C.c_uint64(7), C.c_int(1)
+    hp.L.kxh_snapshot_enable.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    hp.L.kxh_validation_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    hp.L.kxh_snapshot_enable(hp.h, C.byref(gen), C.byref(healthy))
+
+    def counts():
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        hp.L.kxh_validation_counts(hp.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+    hp.init("YAML")
+    want = {"envs": {"KUBERNETES_CDI_VENDOR_CLASS": "nvidia.com/gpu"}, "cdi_devices": ["nvidia.com/gpu=0", "nvidia.com/gpu=1", "nvidia.com/gpu=3"]}
+    assert hp.allocate(["75", "214"]) == want and counts() == (0, 3)
+    # the device is re-bound behind the plugin's back WITHOUT an event: the snapshot still answers (that is the
+    # contract: the kernel announces every re-bind) ...
+    link = os.path.join(base, "0000:c1:00.0", "iommu_group")
+    os.unlink(link)
+    os.symlink(os.path.join(str(tmp_path), "iommu_groups", "215"), link)
+    assert hp.allocate(["214"])["cdi_devices"] == ["nvidia.com/gpu=3"] and counts() == (0, 4)
+    # ... and with the event the live reads run and reject it exactly like the reference
+    gen.value = 8
+    with pytest.raises(RuntimeError, match="invalid allocation request: unknown device: 0000:c1:00.0"):
+        hp.allocate(["214"])
+    assert counts()[0] == 1
+    assert hp.allocate(["75"])["cdi_devices"] == ["nvidia.com/gpu=0", "nvidia.com/gpu=1"] and counts()[0] == 3
+    # an unhealthy watcher (lost messages) also means live reads
+    gen.value, healthy.value = 7, 0
+    assert hp.allocate(["76"])["cdi_devices"] == ["nvidia.com/gpu=2"] and counts()[0] == 4
+    hp.close()
