@@ -13,6 +13,11 @@
  *   - inputs are borrowed for the duration of the call (cgo rule: no Go pointer is
  *     retained); outputs are caller-allocated, `cap` is passed, and when `cap` is too
  *     small the call returns KXPU_E_NOSPACE after storing the required size.
+ *   - two calls take a struct that CONTAINS pointers (kxpu_classify_out: seven output arrays;
+ *     kxpu_shard: device pointers).  From Go the arrays a kxpu_classify_out points at must be
+ *     pinned for the call (runtime.Pinner) or C-allocated: cgo rejects a Go struct holding
+ *     pointers to unpinned Go memory.  kxpu_shard only carries device addresses (not Go
+ *     pointers) and needs nothing.  See INTEGRATION.md.
  *   - opaque handles (kxpu_ctx, kxpu_table) are owned by the library.
  *   - there is NO CPU fallback: without a usable sm_100 GPU kxpu_ctx_create fails with
  *     KXPU_E_NOGPU and nothing else can be called.

@@ -16,6 +16,7 @@ import "C"
 import (
 	"fmt"
 	"os"
+	"runtime"
 	"unsafe"
 )
 
@@ -31,10 +32,16 @@ func kxCheck(ctx *C.kxpu_ctx, what string, rc C.int32_t) error {
 	return fmt.Errorf("%s: %s (%s)", what, C.GoString(C.kxpu_strerror(rc)), C.GoString(C.kxpu_last_error(ctx)))
 }
 
+// The library has no CPU path: without a GPU on the NVIDIA driver kxpu_ctx_create returns
+// KXPU_E_NOGPU.  A node whose GPUs are ALL bound to vfio-pci (the reference's normal deployment)
+// therefore cannot use it; InitiateDevicePlugin calls newKxpu once and, on error, logs it and keeps
+// the stock functions (createIommuDeviceMap, getDeviceName, generateCDISpec are untouched in the
+// tree and selected by `if kx == nil`).  That is the host's choice between two implementations,
+// not a fallback inside the library; after a successful create every kxpu_* error is fatal.
 func newKxpu(ordinal int) (*kxpu, error) {
 	k := &kxpu{}
 	if rc := C.kxpu_ctx_create(C.int32_t(ordinal), &k.ctx); rc != C.KXPU_OK {
-		return nil, fmt.Errorf("kxpu_ctx_create: %s", C.GoString(C.kxpu_strerror(rc))) // fatal: no CPU path
+		return nil, fmt.Errorf("kxpu_ctx_create: %s", C.GoString(C.kxpu_strerror(rc)))
 	}
 	return k, nil
 }
@@ -86,6 +93,10 @@ func (k *kxpu) deviceNames(ids []string) ([]string, error) {
 }
 
 // S1/S4: classify the raw sysfs records gathered by the walk.
+// kxpu_classify_out is a struct of seven output pointers.  `out` itself lives in Go memory, so cgo
+// (cgocheck=1, the default) inspects it and refuses Go pointers to UNPINNED Go memory inside it
+// ("cgo argument has Go pointer to unpinned Go pointer").  runtime.Pinner (Go 1.21+) pins the seven
+// backing arrays for the duration of the call; the library keeps none of them (include/kxpu.h).
 func (k *kxpu) classify(recs []C.kxpu_devrec) (accept, gids, goff, gmem []uint32, dids []uint64, doff, dgrp []uint32, err error) {
 	n := len(recs)
 	accept, gids, goff, gmem = make([]uint32, n), make([]uint32, n), make([]uint32, n+1), make([]uint32, n)
@@ -93,6 +104,15 @@ func (k *kxpu) classify(recs []C.kxpu_devrec) (accept, gids, goff, gmem []uint32
 	if n == 0 {
 		return
 	}
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	pin.Pin(&accept[0])
+	pin.Pin(&gids[0])
+	pin.Pin(&goff[0])
+	pin.Pin(&gmem[0])
+	pin.Pin(&dids[0])
+	pin.Pin(&doff[0])
+	pin.Pin(&dgrp[0])
 	var out C.kxpu_classify_out
 	out.accept_index = (*C.uint32_t)(unsafe.Pointer(&accept[0]))
 	out.group_ids = (*C.uint32_t)(unsafe.Pointer(&gids[0]))
@@ -105,6 +125,28 @@ func (k *kxpu) classify(recs []C.kxpu_devrec) (accept, gids, goff, gmem []uint32
 	gids, goff, gmem = gids[:out.n_groups], goff[:out.n_groups+1], gmem[:out.n_accepted]
 	dids, doff, dgrp = dids[:out.n_devids], doff[:out.n_devids+1], dgrp[:out.n_groups]
 	return
+}
+
+// S2, start-up form: pci.ids text + every device id of deviceMap in ONE call and one host round trip
+// (kxpu_pciids_join: for the 1.4 MB file one cooperative kernel parses, folds, names and joins).
+func (k *kxpu) loadAndJoin(path string, keys []uint32) ([]int32, error) {
+	text, err := os.ReadFile(path)
+	if err != nil {
+		return nil, err
+	}
+	rows := make([]int32, len(keys))
+	var tp *C.uint8_t
+	var kp *C.uint32_t
+	var rp *C.int32_t
+	if len(text) > 0 {
+		tp = (*C.uint8_t)(unsafe.Pointer(&text[0]))
+	}
+	if len(keys) > 0 {
+		kp = (*C.uint32_t)(unsafe.Pointer(&keys[0]))
+		rp = (*C.int32_t)(unsafe.Pointer(&rows[0]))
+	}
+	err = kxCheck(k.ctx, "kxpu_pciids_join", C.kxpu_pciids_join(k.ctx, tp, C.size_t(len(text)), kp, C.size_t(len(keys)), rp, &k.table))
+	return rows, err
 }
 
 // S3: CDI document bytes (format 0 = YAML as the reference's live path, 1 = JSON).

@@ -4,7 +4,8 @@ This package holds only what the hot path needs:
   csrc/      CUDA kernels for sm_100a + the C ABI (include/kxpu.h) -> lib/libkxpu.so
   host/      host-side mirror of the reference's discovery / CDI / Allocate logic (C++)
   binding.py ctypes binding of the C ABI (what the Go cgo shim of INTEGRATION.md does)
-  sharding.py thin wrapper over kxpu_plan_shards (kept for the CPU tests of the shard planner)
+  sharding.py the shard-planning rule in Python (the product planner is kxpu_plan_shards behind the ABI;
+             tests hold the two equal)
   workloads.py synthetic inputs of BASELINE.json configs[0..4]
 
 The directory name contains '-', so import it through the repo-root shim `kxpu_b200`.

@@ -246,11 +246,11 @@ class Kxpu:
         self._chk(self.L.kxpu_pciids_join_device(self.ctx, d_text, n, d_keys, nq, d_rows, C.byref(h)))
         return Table(self, h)
 
-    def pciids_join(self, text, keys):
+    def pciids_join(self, text, keys, rows_out=None):
         """Host text + host keys -> (table, row handles): one call, one host round trip."""
         a = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
         keys = np.ascontiguousarray(keys, dtype=np.uint32)
-        rows = np.empty(len(keys), np.int32)
+        rows = rows_out if rows_out is not None else np.empty(len(keys), np.int32)
         h = C.c_void_p()
         self._chk(self.L.kxpu_pciids_join(self.ctx, a.ctypes.data if a.size else None, a.size, _ptr(keys), len(keys), _ptr(rows),
                                           C.byref(h)))

@@ -56,7 +56,7 @@ int32_t kx_ctx_create_on(int32_t ordinal, kxpu_ctx **out) {
     bool ok = true;
     for (int i = 0; i < 2 * KXPU_T_COUNT; i++) ok = ok && cudaEventCreate(&c->ev[i]) == cudaSuccess;
     ok = ok && cudaEventCreate(&c->ev_user[0]) == cudaSuccess && cudaEventCreate(&c->ev_user[1]) == cudaSuccess;
-    ok = ok && cudaMallocHost((void **)&c->h_ctl, 64 * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&c->h_ctl, (KX_C_COUNT + 64) * sizeof(uint32_t)) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         kxpu_ctx_destroy(c);
@@ -437,8 +437,10 @@ int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, 
         F.blob = slab->blob; F.blob_cap = slab->blob_cap;
     }
     KxTimer tm(ctx, KXPU_T_FINALIZE);
-    // validity + names: one warp per SF_BATCH table slots, persistent grid
-    const unsigned batches = (t->cap + 1 + kxparse::SF_BATCH - 1) / kxparse::SF_BATCH;
+    // validity + names: a warp scans scan_w table slots per step, persistent grid.  Small tables: 8 slots per
+    // warp keep every warp of the grid busy with one short chain; big ones scan 32 and work off full batches
+    F.scan_w = t->cap >= (1u << 19) ? 32u : 8u;
+    const unsigned batches = (t->cap + 1 + F.scan_w - 1) / F.scan_w;
     const unsigned grid = std::min<unsigned>((batches + kxparse::SF_WARPS - 1) / kxparse::SF_WARPS, 8u * ctx->sm_count);
     kxparse::select_finalize_kernel<<<grid, kxparse::SF_WARPS * 32, 0, ctx->stream>>>(F);
     KX_LAUNCHED(ctx);

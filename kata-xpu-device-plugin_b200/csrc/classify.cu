@@ -12,7 +12,7 @@
 //   iommuMap CSR  = accepted records stably sorted by group ordinal -> LSD radix sort
 //   deviceMap     = groups keyed by the device id of their first member, ids ordered by
 //                   first appearance; CSR by a second stable sort.
-// Launches: reset | candidates | accept + both scans (single pass, decoupled look-back) | device-id
+// Launches: reset | candidates | accept + both scans (single pass, decoupled look-back) | per-group device ids | device-id
 // first-seen scan over the groups | sort pairs + all digit histograms | <= 4 radix passes, each ONE
 // kernel for both sorts (per-tile ranking + per-digit look-back, "onesweep") | CSR boundaries.
 #include <algorithm>
@@ -194,23 +194,9 @@ __global__ void __launch_bounds__(C_THREADS) k_accept_scan(const Work W) {
         outv[k] = KXPU_REJECTED;
         if ((accm >> k) & 1u) outv[k] = racc++;
         if ((gfm >> k) & 1u) {
-            const uint32_t i = base + k, ord = rgf++;
-            GSlot &g = W.gtab[slot[k]];
-            g.ord = ord;
-            W.group_ids[ord] = g.key;
-            W.grp_rec[ord] = i;
-            // the group is attributed to the device id of its first member (device_plugin.go:162-170)
-            const uint32_t *rw = reinterpret_cast<const uint32_t *>(W.recs + i);
-            const uint2 dq = make_uint2(rw[6], rw[7]);  // device_txt
-            const uint32_t dlen = (rw[13] >> 8) & 0xffu;
-            unsigned long long did;
-            uint32_t dl;
-            read_id(reinterpret_cast<const uint8_t *>(&dq), dlen, did, dl);
-            const uint32_t ds = dinsert(W, did);
-            // a few hot device ids own most groups: same-address atomics run at ~1 per ns, so only a record that
-            // can still lower the minimum issues one (the early tiles settle it, the rest only load)
-            if (i < __ldcg(&W.dtab[ds].first)) atomicMin(&W.dtab[ds].first, i);
-            W.grp_dslot[ord] = ds;
+            const uint32_t ord = rgf++;
+            W.gtab[slot[k]].ord = ord;
+            W.grp_rec[ord] = base + k;  // the rest of the group's bookkeeping: k_groups, one thread per group
         }
     }
     if (base + C_ITEMS <= W.n) {
@@ -222,6 +208,28 @@ __global__ void __launch_bounds__(C_THREADS) k_accept_scan(const Work W) {
         for (int k = 0; k < C_ITEMS; k++)
             if (base + k < W.n) W.accept_index[base + k] = outv[k];
     }
+}
+
+// pass 2b: one thread per group (ordinal order): the group id and the device id of its first member (the group is
+// attributed to the device id of its FIRST member, device_plugin.go:162-170) -> device-id table, first-seen minimum.
+// Kept out of k_accept_scan: there the chain record read -> table insert -> minimum ran serially per record in a
+// divergent loop (6 % issue utilisation); here every group is an independent thread.
+__global__ void __launch_bounds__(256) k_groups(const Work W) {
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= W.totals[1]) return;
+    const uint32_t i = W.grp_rec[o];
+    const uint32_t *rw = reinterpret_cast<const uint32_t *>(W.recs + i);
+    const uint2 dq = make_uint2(rw[6], rw[7]);  // device_txt
+    const uint32_t dlen = (rw[13] >> 8) & 0xffu;
+    W.group_ids[o] = rw[12];                    // iommu_group
+    unsigned long long did;
+    uint32_t dl;
+    read_id(reinterpret_cast<const uint8_t *>(&dq), dlen, did, dl);
+    const uint32_t ds = dinsert(W, did);
+    // a few hot device ids own most groups: same-address atomics run at ~1 per ns, so only a group that can
+    // still lower the minimum issues one
+    if (i < __ldcg(&W.dtab[ds].first)) atomicMin(&W.dtab[ds].first, i);
+    W.grp_dslot[o] = ds;
 }
 
 // pass 3: over the groups in ordinal order: is this the first group of its device id?  Scan -> device ordinals.
@@ -510,9 +518,10 @@ static int32_t classify_once(kxpu_ctx *ctx, const kxpu_devrec *recs, size_t n, k
             (uint4 *)b, ff_bytes / 16, W.totals, (uint32_t)zero_words);
         k_candidates<<<g, 256, 0, ctx->stream>>>(W);
         k_accept_scan<<<c_tiles, C_THREADS, 0, ctx->stream>>>(W);
+        k_groups<<<g, 256, 0, ctx->stream>>>(W);
         k_devfirst_scan<<<c_tiles, C_THREADS, 0, ctx->stream>>>(W);
         k_pairs<<<std::min<unsigned>(g, 4u * ctx->sm_count), 256, 0, ctx->stream>>>(W, passes);
-        ctx->launches += 5;
+        ctx->launches += 6;
         for (uint32_t p = 0; p < passes; p++) {
             SweepParams S;
             S.shift = 8 * p;

@@ -689,7 +689,7 @@ static void shard_phase4(ShardOp &op) {
     }
     g_trace.mark(9, ctx->stream);
     cudaMemcpyAsync(ctx->h_ctl, op.t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    if (!op.nccl) cudaMemcpyAsync(ctx->h_ctl + 32, x->scratch + 8, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (!op.nccl) cudaMemcpyAsync(ctx->h_ctl + KX_C_COUNT, x->scratch + 8, 4, cudaMemcpyDeviceToHost, ctx->stream);
 }
 
 enum { SH_DONE = 0, SH_RETRY = 1, SH_FAIL = 2 };
@@ -720,7 +720,7 @@ static int shard_complete(ShardOp &op, kxpu_table **out, int32_t *rc_out) {
     if (op.a.nq_total && x->ipc) g_trace.report(x->rank, x->nranks);
     const uint32_t *h = ctx->h_ctl;
     const uint32_t st = h[KX_C_XSTATUS];
-    if ((st & 0x80000000u) || (!op.nccl && h[32])) {
+    if ((st & 0x80000000u) || (!op.nccl && h[KX_C_COUNT])) {
         KX_SET_ERR(ctx, "peer-memory exchange: a rank did not deliver within 4 s (epoch %u)", op.epoch);
         x->broken = true;
         cudaMemsetAsync(x->scratch + 8, 0, 4, ctx->stream);

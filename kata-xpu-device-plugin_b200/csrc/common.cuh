@@ -38,7 +38,7 @@ struct kxpu_ctx {
     std::mutex mu;
     char err[512] = {0};
     // pinned staging for small H2D/D2H control words
-    uint32_t *h_ctl = nullptr;  // 64 words, pinned
+    uint32_t *h_ctl = nullptr;  // KX_C_COUNT + 64 words, pinned
     // table arenas: released tables park their (already reset) arena here
     std::vector<KxArena> pool;
     uint32_t cap_hint = 1u << 16;       // table capacity the next load starts with (follows the last text)

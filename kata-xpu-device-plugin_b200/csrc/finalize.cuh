@@ -98,8 +98,7 @@ __device__ __forceinline__ uint32_t sanitise_byte(const uint8_t *buf, uint32_t i
 
 constexpr int SF_WARPS = 8;
 constexpr int SF_WIN = 128;  // bytes of a line a row group looks at (eight lanes x one aligned 16-byte load)
-constexpr int SF_BATCH = 8;  // table slots per warp and step: ~30 % are valid, so a step is usually ONE round of four rows --
-                             // small batches keep ~8 000 warps in flight, each with a single chain of dependent loads
+constexpr int SF_BATCH = 8;  // rows a warp works off per step (two rounds of four rows)
 
 struct FinalizeParams {
     const uint8_t *text;  // shard text (local)
@@ -118,6 +117,7 @@ struct FinalizeParams {
     kxx::WaitSpec wait;       // sharded load: the all-reduced minima are complete when these flags are up
     kxx::SlabRow *slab_rows;  // sharded load: rows go here (this rank's slab, 32-byte records) instead of the row arrays
     uint32_t slab_rows_cap;
+    uint32_t scan_w;          // table slots a warp scans per step: 8 (latency) or 32 (big tables)
 };
 
 __device__ __forceinline__ void finalize_store_row(const FinalizeParams &F, uint32_t row, uint32_t slot, uint32_t key, unsigned long long line,
@@ -135,85 +135,106 @@ __device__ __forceinline__ void finalize_store_row(const FinalizeParams &F, uint
     }
 }
 
-// Validity + names in ONE kernel.  A warp takes SF_BATCH consecutive table slots; the valid ones
-// (min_anchor == first anchor of the vendor, line in front of the ErrTooLong cut-off) are worked off
-// four at a time, eight lanes per row: one aligned 16-byte load per lane brings 128 bytes of the
-// line, the lanes find the newline, trim (strings.TrimSpace), sanitise their 16 bytes each
-// (device_plugin.go:241-251) and compact the result into a shared-memory staging row.  Per batch the
-// warp claims row handles and blob space with one atomic each and copies the names out.  Lines whose
-// rest does not end inside the window (never in device lines of pci.ids' NVIDIA block) take a serial
-// path.  KX_C_NEED_TRUNC: 0 = cut-off never computed, 1 = computed (trunc_kernel), 2 = asked for:
-// when the parse raised the long-line hint and the cut-off is not there yet, every block leaves
-// (the test does not depend on what block 0 writes) and the host finalizes again.
-__device__ __forceinline__ void select_finalize_body(const FinalizeParams &F) {
+// Validity + names in ONE kernel.  A warp scans `scan_w` consecutive table slots per step (8 for the
+// small tables of pci.ids-sized vendor sets: ~8 000 warps each with a single chain of dependent loads;
+// 32 for big tables, where the kernel is throughput bound) and queues the valid ones (min_anchor ==
+// first anchor of the vendor, line in front of the ErrTooLong cut-off) in shared memory, prefetching
+// their name windows into L2.  Queued rows are worked off SF_BATCH at a time -- full batches as long as
+// the warp has slots left to scan, the remainder at the end -- four rows per round, eight lanes per
+// row: one aligned 16-byte load per lane brings 128 bytes of the line, the lanes find the newline, trim
+// (strings.TrimSpace), sanitise one byte per lane and step (device_plugin.go:241-251) and compact the
+// result into a shared-memory staging row.  Per batch the CTA claims row handles and blob space with one
+// atomic each and the warps copy the names out.  Lines whose rest does not end inside the window (19
+// device lines of pci.ids) are taken by the whole warp one at a time.  KX_C_NEED_TRUNC: 0 = cut-off
+// never computed, 1 = computed (trunc_kernel), 2 = asked for: when the parse raised the long-line hint
+// and the cut-off is not there yet, every block leaves (the test does not depend on what block 0
+// writes) and the host finalizes again.
+struct SfEntry {
+    unsigned long long line, anchor;
+    uint32_t slot, key;
+};
+constexpr int SF_QCAP = SF_BATCH - 1 + 32;  // what is left of the queue + one scan
+
+__device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, const uint32_t scan_w) {
     __shared__ __align__(16) uint8_t s_raw[SF_WARPS][4][SF_WIN + 16];
     __shared__ uint8_t s_name[SF_WARPS][SF_BATCH][SF_WIN];
-    __shared__ uint32_t s_cnt[SF_WARPS], s_bytes[SF_WARPS], s_row0, s_blob0;
+    __shared__ __align__(8) SfEntry s_q[SF_WARPS][SF_QCAP + 1];
+    __shared__ uint32_t s_cnt[SF_WARPS], s_bytes[SF_WARPS], s_more[SF_WARPS], s_row0, s_blob0;
     if (F.tab.counters[KX_C_LONGLINE_HINT] != 0u && F.tab.counters[KX_C_NEED_TRUNC] != 1u) {
         if (blockIdx.x == 0 && threadIdx.x == 0) F.tab.counters[KX_C_NEED_TRUNC] = 2u;
         return;
     }
     const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5, sub = lane & 7u, grp = lane >> 3;
     const uint32_t nslots = F.tab.cap + 1u;
+    const uint32_t nchunks = (nslots + scan_w - 1u) / scan_w;
+    const uint32_t cstride = gridDim.x * (uint32_t)SF_WARPS;
     const unsigned long long trunc = kxx::min_view_trunc(F.mv);
+    SfEntry *q = s_q[wl];
+    uint32_t chunk = blockIdx.x * (uint32_t)SF_WARPS + wl;  // the CTA's warps take neighbouring chunks
+    uint32_t qn = 0;                                        // queued rows of this warp
     // the CTA's warps step together: row handles and blob space are claimed once per CTA and step
     // (same-address atomics run at ~1 per ns: one pair per warp and step was the whole kernel time)
-    for (uint32_t c0 = blockIdx.x * SF_WARPS * (uint32_t)SF_BATCH; c0 < nslots; c0 += gridDim.x * SF_WARPS * (uint32_t)SF_BATCH) {
-        const uint32_t s0 = c0 + wl * (uint32_t)SF_BATCH;
-        const uint32_t slot = s0 + lane;
-        bool valid = false;
-        uint32_t key = 0;
-        unsigned long long line = 0, anchor = 0;
-        if (lane < (uint32_t)SF_BATCH && slot < nslots) {
-            const uint4 head = *reinterpret_cast<const uint4 *>(&F.tab.slots[slot]);
-            line = ((unsigned long long)head.w << 32) | head.z;
-            key = slot == F.tab.cap ? KX_EMPTY_KEY : head.x;
-            valid = line != KX_NO_OFF && !(slot < F.tab.cap && key == KX_EMPTY_KEY);
-            if (valid) {
-                anchor = F.tab.slots[slot].min_anchor;
-                valid = anchor == kxx::min_view_first(F.mv, key >> 16) && line < trunc;
+    for (;;) {
+        if (qn < (uint32_t)SF_BATCH && chunk < nchunks) {
+            const uint32_t slot = chunk * scan_w + lane;
+            chunk += cstride;
+            bool valid = false;
+            uint32_t key = 0;
+            unsigned long long line = 0, anchor = 0;
+            if (lane < scan_w && slot < nslots) {
+                const uint4 head = *reinterpret_cast<const uint4 *>(&F.tab.slots[slot]);
+                line = ((unsigned long long)head.w << 32) | head.z;
+                key = slot == F.tab.cap ? KX_EMPTY_KEY : head.x;
+                valid = line != KX_NO_OFF && !(slot < F.tab.cap && key == KX_EMPTY_KEY);
+                if (valid) {
+                    anchor = F.tab.slots[slot].min_anchor;
+                    valid = anchor == kxx::min_view_first(F.mv, key >> 16) && line < trunc;
+                }
             }
+            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                SfEntry e;
+                e.line = line; e.anchor = anchor; e.slot = slot; e.key = key;
+                q[qn + (uint32_t)__popc(vm & ((1u << lane) - 1u))] = e;
+                // the name window of this row: on its way into L2 while the queue fills up
+                const unsigned long long a0 = (line - F.base + 5ull) & ~15ull;
+                if (a0 < F.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.text + a0));
+                if (a0 + 112ull < F.n && ((a0 + 112ull) >> 7) != (a0 >> 7)) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.text + a0 + 112ull));
+            }
+            qn += (uint32_t)__popc(vm);
+            __syncwarp();
         }
-        const uint32_t vm = __ballot_sync(0xffffffffu, valid);
-        const uint32_t nvalid = (uint32_t)__popc(vm);
-        const uint32_t myrank = (uint32_t)__popc(vm & ((1u << lane) - 1u));  // row of this lane's slot inside the batch
+        const bool have = chunk < nchunks;
+        const uint32_t nvalid = qn >= (uint32_t)SF_BATCH ? (uint32_t)SF_BATCH : (have ? 0u : qn);  // rows of this batch: queue[0, nvalid)
         uint32_t my_len = 0;    // lane r (< nvalid): sanitised length of batch row r
-        uint32_t slow_m = 0;    // batch rows that need the serial path
+        uint32_t slow_m = 0;    // batch rows that need the long-line path
         for (uint32_t r0 = 0; r0 < nvalid; r0 += 4u) {
             const uint32_t r = r0 + grp;  // batch row of my group
             const bool act = r < nvalid;
-            // the lane that owns batch row r0 + g (its myrank-th valid slot), for the four groups
-            uint32_t src = 0;
-#pragma unroll
-            for (uint32_t g = 0; g < 4u; g++) {
-                const uint32_t own = __ballot_sync(0xffffffffu, valid && myrank == r0 + g);
-                if (grp == g && own) src = (uint32_t)__ffs((int)own) - 1u;
-            }
-            const unsigned long long rline = __shfl_sync(0xffffffffu, line, src);
             const uint32_t gmask = 0xffu << (8u * grp);  // my row group: its eight lanes take every branch below together
             uint32_t total = 0, start = 0, end = 0;
             bool slow = false;
             const uint8_t *buf = s_raw[wl][grp];
             if (act) {
-                const unsigned long long rs = rline - F.base + 5ull;  // rest of the line after "\t" + 4 hex digits
+                const unsigned long long rs = q[r].line - F.base + 5ull;  // rest of the line after "\t" + 4 hex digits
                 const unsigned long long a0 = rs & ~15ull;
                 const uint32_t lead = (uint32_t)(rs - a0);
                 const unsigned long long p0 = a0 + 16ull * sub;
-                uint4 q;
+                uint4 qd;
                 if (p0 + 16ull <= F.n) {
-                    q = *reinterpret_cast<const uint4 *>(F.text + p0);
+                    qd = *reinterpret_cast<const uint4 *>(F.text + p0);
                 } else {
                     uint8_t tmp[16];
 #pragma unroll
                     for (int k = 0; k < 16; k++) tmp[k] = p0 + k < F.n ? F.text[p0 + k] : (uint8_t)0x0a;  // EOF terminates the last line
-                    q = *reinterpret_cast<uint4 *>(tmp);
+                    qd = *reinterpret_cast<uint4 *>(tmp);
                 }
                 uint8_t *raw = s_raw[wl][grp];
-                *reinterpret_cast<uint4 *>(raw + 16u * sub) = q;
+                *reinterpret_cast<uint4 *>(raw + 16u * sub) = qd;
                 // first newline at or behind `lead`: SWAR byte-equality mask of my 16 bytes (bit k = byte k is '\n')
                 uint32_t nlm = 0;
                 {
-                    const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+                    const uint32_t w4[4] = {qd.x, qd.y, qd.z, qd.w};
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const uint32_t y = w4[k] ^ 0x0a0a0a0au;
@@ -285,7 +306,7 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F) {
             if (lane >= (uint32_t)d) incl += y;
         }
         const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
-        if (lane == 0) { s_cnt[wl] = nvalid; s_bytes[wl] = wtot; }
+        if (lane == 0) { s_cnt[wl] = nvalid; s_bytes[wl] = wtot; s_more[wl] = (have || qn > nvalid) ? 1u : 0u; }
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t rows = 0, bytes = 0;
@@ -297,8 +318,10 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F) {
             s_blob0 = b0;
         }
         __syncthreads();
-        uint32_t row0 = s_row0, blob0 = s_blob0;
+        uint32_t row0 = s_row0, blob0 = s_blob0, more = 0;
         for (uint32_t k = 0; k < wl; k++) { row0 += s_cnt[k]; if (blob0 != 0xFFFFFFFFu) blob0 += s_bytes[k]; }
+#pragma unroll
+        for (int k = 0; k < SF_WARPS; k++) more |= s_more[k];
         const bool room = blob0 != 0xFFFFFFFFu;
         const uint32_t off_r = room ? blob0 + incl - len_r : 0u;
         // names out: one row at a time, 32 bytes per step
@@ -307,21 +330,19 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F) {
             if (room)
                 for (uint32_t j = lane; j < L; j += 32u) F.blob[O + j] = s_name[wl][r][j];
         }
-        // row records: the lane that owns the slot writes its row (batch row = myrank)
-        const uint32_t my_row_len = __shfl_sync(0xffffffffu, len_r, valid ? myrank : 0u);
-        const uint32_t my_row_off = __shfl_sync(0xffffffffu, off_r, valid ? myrank : 0u);
-        const bool my_slow = valid && ((slow_m >> myrank) & 1u);
-        if (valid && !my_slow) finalize_store_row(F, row0 + myrank, slot, key, line, anchor, room ? my_row_off : 0u, room ? my_row_len : 0u);
+        // row records: lane r writes batch row r
+        if (lane < nvalid && !((slow_m >> lane) & 1u)) {
+            const SfEntry e = q[lane];
+            finalize_store_row(F, row0 + lane, e.slot, e.key, e.line, e.anchor, room ? off_r : 0u, room ? len_r : 0u);
+        }
         // long lines (the rest does not end inside the 128-byte window; 19 device lines of pci.ids):
         // the whole warp takes them one at a time -- the line is staged into the (now free) name staging
         // area 32 bytes per step, then sanitised one byte per lane with ballot compaction
         __syncwarp();
         for (uint32_t sm = slow_m; sm; sm &= sm - 1u) {
             const uint32_t r = (uint32_t)__ffs((int)sm) - 1u;
-            const uint32_t own = __ballot_sync(0xffffffffu, valid && myrank == r);
-            const uint32_t ol = (uint32_t)__ffs((int)own) - 1u;
-            const unsigned long long l_line = __shfl_sync(0xffffffffu, line, ol), l_anchor = __shfl_sync(0xffffffffu, anchor, ol);
-            const uint32_t l_key = __shfl_sync(0xffffffffu, key, ol), l_slot = __shfl_sync(0xffffffffu, slot, ol);
+            const unsigned long long l_line = q[r].line, l_anchor = q[r].anchor;
+            const uint32_t l_key = q[r].key, l_slot = q[r].slot;
             const unsigned long long rs = l_line - F.base + 5ull;
             uint8_t *buf = &s_name[wl][0][0];
             constexpr uint32_t LONG_MAX_LEN = (uint32_t)(SF_BATCH * SF_WIN) - 32u;
@@ -386,13 +407,26 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F) {
             if (lane == 0) finalize_store_row(F, row0 + r, l_slot, l_key, l_line, l_anchor, ok ? at : 0u, ok ? out_len : 0u);
             __syncwarp();
         }
+        // what is left of the queue moves to its front
+        {
+            const uint32_t rem = qn - nvalid;
+            if (nvalid != 0u && rem != 0u) {
+                SfEntry e;
+                if (lane < rem) e = q[nvalid + lane];
+                __syncwarp();
+                if (lane < rem) q[lane] = e;
+                __syncwarp();
+            }
+            qn = rem;
+        }
         __syncthreads();  // the staging rows and the claim words are reused by the next step
+        if (!more) break;
     }
 }
 
 __global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const FinalizeParams F) {
     kxx::wait_flags_cta(F.wait);
-    select_finalize_body(F);
+    select_finalize_body(F, F.scan_w);
 }
 
 // ------------------------------------------------------------------------------

@@ -172,6 +172,9 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
             rc_g = 0xffffffffu;
         }
         uint32_t lead = r == 0u ? 0u : rch;  // chunks whose head lines nobody can judge yet
+        // the table ran full (the host grows it and parses again): fold nothing more.  Looked at once per
+        // range, early, so that nobody waits for it; a stale answer costs bounded probing (KX_MAX_PROBE)
+        const bool table_dead = *reinterpret_cast<volatile uint32_t *>(&P.tab.counters[KX_C_OVERFLOW]) != 0u;
         const uint32_t gb = r * rch;
         const uint32_t cnt = P.num_chunks - gb < rch ? P.num_chunks - gb : rch;
         if (!staged && lane == 0) {
@@ -241,8 +244,6 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
                 uint32_t kh[2];
                 kh[0] = th[0] | devs_of(st + lane * 32u + 1u, nl[0] & ~th[0]);
                 kh[1] = th[1] | devs_of(st + (uint32_t)HALF + lane * 32u + 1u, nl[1] & ~th[1]);
-                // the table ran full (the host grows it and parses again): fold nothing more
-                const bool table_dead = *reinterpret_cast<volatile uint32_t *>(&P.tab.counters[KX_C_OVERFLOW]) != 0u;
                 if (table_dead) { kh[0] = th[0]; kh[1] = th[1]; }
 
                 // the shard starts with a line start at p = 0 (no newline before it)
@@ -408,15 +409,26 @@ __global__ void __launch_bounds__(256) resolve_ranges_kernel(const Params5 P) {
             q0 -= 32;  // q == -1 (the shard's carry-in) always answers: the loop ends at the latest there
         }
     }
-    if (nlead == 0u) return;
     // no top-level line between the start of the range and those chunks' head lines: the carry
     // into the range governs them
     const unsigned long long carry = (below ? from_warp : warp_in) & ~ST_MASK;
-    const bool alive = (carry & CV_HAS_TOP) && (carry & CV_VOK) &&
+    const bool alive = nlead != 0u && (carry & CV_HAS_TOP) && (carry & CV_VOK) &&
                        P.tab.vendor_first[(uint32_t)(carry >> 44) & 0xffffu] >= (carry & CV_ANCHOR_MASK);  // vendor_first is final here
+    // queue space: one atomic per warp (in a text without repeated blocks every range queues its chunks)
+    const uint32_t mine = alive ? nlead : 0u;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += y;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t at0 = 0;
+    if (lane == 0 && tot) at0 = atomicAdd(&P.tab.counters[KX_C_DEFER], tot);
+    at0 = __shfl_sync(0xffffffffu, at0, 0);
     if (!alive) return;
     P.range_carry[rr] = carry;
-    const uint32_t at = atomicAdd(&P.tab.counters[KX_C_DEFER], nlead);
+    const uint32_t at = at0 + incl - mine;
     for (uint32_t j = 0; j < nlead; j++) P.tasks[at + j] = rr * P.rch + j;
 }
 
@@ -438,8 +450,10 @@ __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Pa
     const unsigned long long pol = l2_evict_first_policy();
     const uint32_t n_tasks = P.tab.counters[KX_C_DEFER];
     uint32_t par = 0, nfresh = 0;
-    for (uint32_t t = blockIdx.x * RES_WARPS + w; t < n_tasks; t += gridDim.x * RES_WARPS) {
-        if (*reinterpret_cast<volatile uint32_t *>(&P.tab.counters[KX_C_OVERFLOW]) != 0u) break;  // table full: the host parses again
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x * RES_WARPS + w; t < n_tasks; t += gridDim.x * RES_WARPS, it++) {
+        // table full: the host grows it and parses again (polled every fourth task: a stale answer costs bounded probing)
+        if ((it & 3u) == 0u && *reinterpret_cast<volatile uint32_t *>(&P.tab.counters[KX_C_OVERFLOW]) != 0u) break;
         const uint32_t gg = P.tasks[t];
         uint32_t n_rel = CW + 1;
         if (gg < P.tma_limit) {

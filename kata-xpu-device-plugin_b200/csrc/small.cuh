@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(NT, 4) small_load_kernel(const SmallParams P) 
     grid_barrier(&tab.counters[KX_C_GRIDBAR], 2u * gridDim.x);
 
     // ---------------------------------------------------------------- phase 3
-    select_finalize_body(P.F);
+    select_finalize_body(P.F, 8u);
     if (P.nq == 0) return;
     grid_barrier(&tab.counters[KX_C_GRIDBAR], 3u * gridDim.x);
 

@@ -23,23 +23,26 @@
 #define KX_EMPTY_KEY 0xFFFFFFFFu
 #define KX_NO_OFF 0xFFFFFFFFFFFFFFFFull
 
-// counters[] indices
-#define KX_C_TICKET 0
-#define KX_C_NKEYS 1
-#define KX_C_OVERFLOW 2
-#define KX_C_LONGLINE_HINT 3
-#define KX_C_NROWS 4
-#define KX_C_BLOB_CURSOR 5
-#define KX_C_BLOB_OVERFLOW 6
-#define KX_C_NEED_TRUNC 7
-#define KX_C_GRIDBAR 8   // small-text kernel: grid barrier arrivals
-#define KX_C_NSEL 9
-#define KX_C_DEFER 10
-#define KX_C_XSTATUS 11   // sharded load: KX_XS_* bits, identical on every rank after the exchange
-#define KX_C_XROWS 12     // sharded load: winner rows of all ranks
-#define KX_C_XBLOB 13     // sharded load: name bytes of all ranks
-#define KX_C_XMAXKEYS 14  // sharded load: max over ranks of the local candidate key count
-#define KX_C_COUNT 16
+// counters[] indices.  Four 128-byte lines: words that are hammered with atomics at the same time sit on
+// different lines, and the flags that are only polled (OVERFLOW: once per range / task by every warp) have
+// a line of their own -- a load of a line under same-address atomic fire queues behind the atomics (the
+// poll was 36 % of the stall samples of resolve_chunks_kernel when it shared a line with NKEYS).
+#define KX_C_TICKET 0     // line 0: parse range tickets
+#define KX_C_DEFER 1      //         resolve queue length
+#define KX_C_GRIDBAR 2    //         small-text kernel: grid barrier arrivals
+#define KX_C_NKEYS 32     // line 1: claimed slots (parse, resolve, merge)
+#define KX_C_NSEL 33      //         row handles (finalize)
+#define KX_C_BLOB_CURSOR 64   // line 2: name bytes (finalize)
+#define KX_C_OVERFLOW 96      // line 3: flags and results, written rarely
+#define KX_C_LONGLINE_HINT 97
+#define KX_C_NROWS 98
+#define KX_C_BLOB_OVERFLOW 99
+#define KX_C_NEED_TRUNC 100
+#define KX_C_XSTATUS 101   // sharded load: KX_XS_* bits, identical on every rank after the exchange
+#define KX_C_XROWS 102     // sharded load: winner rows of all ranks
+#define KX_C_XBLOB 103     // sharded load: name bytes of all ranks
+#define KX_C_XMAXKEYS 104  // sharded load: max over ranks of the local candidate key count
+#define KX_C_COUNT 128
 
 struct __align__(32) KxSlot {
     uint32_t key;
