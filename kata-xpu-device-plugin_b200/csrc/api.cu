@@ -73,6 +73,7 @@ int32_t kx_ctx_create_on(int32_t ordinal, kxpu_ctx **out) {
     const char *fr = getenv("KXPU_RCH");
     c->force_rch = (fr && fr[0] >= '1' && fr[0] <= '8' && !fr[1]) ? fr[0] - '0' : 0;
     c->no_small = getenv("KXPU_NO_SMALL") != nullptr;
+    if (const char *sw = getenv("KXPU_SCAN_W")) { const int v = atoi(sw); c->force_scan_w = (v == 8 || v == 16 || v == 32) ? v : 0; }
     *out = c;
     return KXPU_OK;
 }
@@ -440,6 +441,7 @@ int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, 
     // validity + names: a warp scans scan_w table slots per step, persistent grid.  Small tables: 8 slots per
     // warp keep every warp of the grid busy with one short chain; big ones scan 32 and work off full batches
     F.scan_w = t->cap >= (1u << 19) ? 32u : 8u;
+    if (ctx->force_scan_w) F.scan_w = (uint32_t)ctx->force_scan_w;
     const unsigned batches = (t->cap + 1 + F.scan_w - 1) / F.scan_w;
     const unsigned grid = std::min<unsigned>((batches + kxparse::SF_WARPS - 1) / kxparse::SF_WARPS, 8u * ctx->sm_count);
     kxparse::select_finalize_kernel<<<grid, kxparse::SF_WARPS * 32, 0, ctx->stream>>>(F);
@@ -501,9 +503,70 @@ static int32_t launch_small(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text,
     void *args[] = {&P};
     // the whole resident grid: phases 1 / 2 use one warp per chunk, the names and the join every warp
     const unsigned grid = std::max<unsigned>((P.num_chunks + WARPS - 1) / WARPS, (unsigned)(ctx->small_chunks / WARPS));
-    KxTimer tm(ctx, KXPU_T_PARSE);
-    KX_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kxsmall::small_load_kernel, dim3(grid), dim3(NT), args, (size_t)WARPS * STG_BYTES, ctx->stream));
-    KX_LAUNCHED(ctx);
+    // names phase: as few table slots per warp and step as give every warp of the grid at most one step
+    F.scan_w = 8u;
+    while (F.scan_w < 32u && (size_t)(t->cap + 1 + F.scan_w - 1) / F.scan_w > (size_t)grid * SF_WARPS) F.scan_w *= 2u;
+    if (ctx->force_scan_w) F.scan_w = (uint32_t)ctx->force_scan_w;
+    // KXPU_TRACE_SMALL=1 (debug): SM clocks at the phase boundaries of every CTA, printed per launch
+    static const bool trace_on = getenv("KXPU_TRACE_SMALL") != nullptr;
+    long long *d_trace = nullptr;
+    if (trace_on && cudaMalloc((void **)&d_trace, (size_t)grid * 128 + (size_t)P.num_chunks * 32) == cudaSuccess) { cudaMemset(d_trace, 0, (size_t)grid * 128 + (size_t)P.num_chunks * 32); P.trace = d_trace; P.F.trace = d_trace + (size_t)grid * 8 + (size_t)P.num_chunks * 4; }
+    {
+        KxTimer tm(ctx, KXPU_T_PARSE);
+        KX_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kxsmall::small_load_kernel, dim3(grid), dim3(NT), args, (size_t)WARPS * STG_BYTES, ctx->stream));
+        KX_LAUNCHED(ctx);
+    }
+    if (d_trace) {
+        std::vector<long long> h((size_t)grid * 16 + (size_t)P.num_chunks * 4);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(d_trace);
+        static const char *nm[7] = {"phase1", "barrier1", "phase2", "barrier2", "names", "barrier3", "join"};
+        fprintf(stderr, "[kxpu small trace] %u CTAs, cycles min/avg/max per CTA:", grid);
+        for (int k = 0; k < 7; k++) {
+            long long mn = 1ll << 62, mx = 0, sum = 0, cnt = 0;
+            for (unsigned b = 0; b < grid; b++) {
+                if (!h[b * 8 + k + 1] || !h[b * 8 + k]) continue;
+                const long long d = h[b * 8 + k + 1] - h[b * 8 + k];
+                mn = std::min(mn, d); mx = std::max(mx, d); sum += d; cnt++;
+            }
+            if (cnt) fprintf(stderr, " %s %lld/%lld/%lld |", nm[k], mn, sum / cnt, mx);
+        }
+        {   // the slowest CTAs of phase 2 (chunks 8*b .. 8*b+7)
+            std::vector<std::pair<long long, unsigned>> v;
+            for (unsigned b = 0; b < grid; b++) v.push_back({h[b * 8 + 3] - h[b * 8 + 2], b});
+            std::sort(v.rbegin(), v.rend());
+            fprintf(stderr, " slowest phase2 CTAs:");
+            for (int k = 0; k < 6 && k < (int)v.size(); k++) fprintf(stderr, " %u:%lld", v[k].second, v[k].first);
+            // per chunk warp: cycles of phase 2, of its part in front of the folds, fold-list entries, look-back steps
+            std::vector<std::pair<long long, unsigned>> wv;
+            const long long *tw = h.data() + (size_t)grid * 8;
+            for (unsigned c = 0; c < P.num_chunks; c++) wv.push_back({tw[c * 4], c});
+            std::sort(wv.rbegin(), wv.rend());
+            fprintf(stderr, "\n   slowest phase2 warps (chunk: cycles / before folds / entries / look-back steps):");
+            for (int k = 0; k < 10 && k < (int)wv.size(); k++) {
+                const unsigned c = wv[k].second;
+                fprintf(stderr, " %u: %lld/%lld/%lld/%lld |", c, tw[c * 4], tw[c * 4 + 1], tw[c * 4 + 2], tw[c * 4 + 3]);
+            }
+            const unsigned mid = wv[wv.size() / 2].second;
+            fprintf(stderr, " median %u: %lld/%lld/%lld/%lld", mid, tw[mid * 4], tw[mid * 4 + 1], tw[mid * 4 + 2], tw[mid * 4 + 3]);
+            // names phase, thread 0 of every CTA: start(=mark 4 of the kernel) -> scan -> rounds -> claim -> sync -> out -> long lines -> end
+            const long long *tf = h.data() + (size_t)grid * 8 + (size_t)P.num_chunks * 4;
+            static const char *fn[7] = {"scan", "rounds", "sync1+claim", "sync2", "names out+rows", "long lines", "shift+sync3"};
+            fprintf(stderr, "\n   names phase per CTA (thread 0), cycles min/avg/max:");
+            for (int k = 0; k < 7; k++) {
+                long long mn = 1ll << 62, mx = 0, sum = 0, cnt = 0;
+                for (unsigned b = 0; b < grid; b++) {
+                    const long long t1 = tf[b * 8 + k], t0 = k ? tf[b * 8 + k - 1] : h[b * 8 + 4];
+                    if (!t1 || !t0) continue;
+                    const long long d = t1 - t0;
+                    mn = std::min(mn, d); mx = std::max(mx, d); sum += d; cnt++;
+                }
+                if (cnt) fprintf(stderr, " %s %lld/%lld/%lld |", fn[k], mn, sum / cnt, mx);
+            }
+        }
+        fprintf(stderr, "\n");
+    }
     return KXPU_OK;
 }
 

@@ -118,6 +118,7 @@ struct FinalizeParams {
     kxx::SlabRow *slab_rows;  // sharded load: rows go here (this rank's slab, 32-byte records) instead of the row arrays
     uint32_t slab_rows_cap;
     uint32_t scan_w;          // table slots a warp scans per step: 8 (latency) or 32 (big tables)
+    long long *trace;         // debug (KXPU_TRACE_SMALL): [gridDim.x][8] clock64 of thread 0 inside the first step
 };
 
 __device__ __forceinline__ void finalize_store_row(const FinalizeParams &F, uint32_t row, uint32_t slot, uint32_t key, unsigned long long line,
@@ -155,6 +156,8 @@ struct SfEntry {
 };
 constexpr int SF_QCAP = SF_BATCH - 1 + 32;  // what is left of the queue + one scan
 
+#define SF_MARK(k) do { if (F.trace && threadIdx.x == 0 && F.trace[blockIdx.x * 8u + (k)] == 0) F.trace[blockIdx.x * 8u + (k)] = clock64(); } while (0)
+
 __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, const uint32_t scan_w) {
     __shared__ __align__(16) uint8_t s_raw[SF_WARPS][4][SF_WIN + 16];
     __shared__ uint8_t s_name[SF_WARPS][SF_BATCH][SF_WIN];
@@ -175,19 +178,25 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, co
     // the CTA's warps step together: row handles and blob space are claimed once per CTA and step
     // (same-address atomics run at ~1 per ns: one pair per warp and step was the whole kernel time)
     for (;;) {
-        if (qn < (uint32_t)SF_BATCH && chunk < nchunks) {
+        while (qn < (uint32_t)SF_BATCH && chunk < nchunks) {  // scan until a full batch is queued (or nothing is left)
             const uint32_t slot = chunk * scan_w + lane;
             chunk += cstride;
             bool valid = false;
             uint32_t key = 0;
             unsigned long long line = 0, anchor = 0;
             if (lane < scan_w && slot < nslots) {
+                // the slot is one 32-byte sector: both halves are asked for at once
                 const uint4 head = *reinterpret_cast<const uint4 *>(&F.tab.slots[slot]);
+                anchor = F.tab.slots[slot].min_anchor;
                 line = ((unsigned long long)head.w << 32) | head.z;
                 key = slot == F.tab.cap ? KX_EMPTY_KEY : head.x;
                 valid = line != KX_NO_OFF && !(slot < F.tab.cap && key == KX_EMPTY_KEY);
                 if (valid) {
-                    anchor = F.tab.slots[slot].min_anchor;
+                    // the name window of a candidate row: on its way into L2 while its first anchor is looked up
+                    // (a candidate that loses wastes one prefetch)
+                    const unsigned long long a0 = (line - F.base + 5ull) & ~15ull;
+                    if (a0 < F.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.text + a0));
+                    if (a0 + 112ull < F.n && ((a0 + 112ull) >> 7) != (a0 >> 7)) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.text + a0 + 112ull));
                     valid = anchor == kxx::min_view_first(F.mv, key >> 16) && line < trunc;
                 }
             }
@@ -196,14 +205,11 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, co
                 SfEntry e;
                 e.line = line; e.anchor = anchor; e.slot = slot; e.key = key;
                 q[qn + (uint32_t)__popc(vm & ((1u << lane) - 1u))] = e;
-                // the name window of this row: on its way into L2 while the queue fills up
-                const unsigned long long a0 = (line - F.base + 5ull) & ~15ull;
-                if (a0 < F.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.text + a0));
-                if (a0 + 112ull < F.n && ((a0 + 112ull) >> 7) != (a0 >> 7)) asm volatile("prefetch.global.L2 [%0];" ::"l"(F.text + a0 + 112ull));
             }
             qn += (uint32_t)__popc(vm);
             __syncwarp();
         }
+        SF_MARK(0);
         const bool have = chunk < nchunks;
         const uint32_t nvalid = qn >= (uint32_t)SF_BATCH ? (uint32_t)SF_BATCH : (have ? 0u : qn);  // rows of this batch: queue[0, nvalid)
         uint32_t my_len = 0;    // lane r (< nvalid): sanitised length of batch row r
@@ -297,6 +303,7 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, co
                 if ((gslow >> (8u * g)) & 1u) slow_m |= 1u << (r0 + g);
         }
         __syncwarp();
+        SF_MARK(1);
         // one claim of row handles and of blob space per batch
         uint32_t len_r = (lane < nvalid && !((slow_m >> lane) & 1u)) ? my_len : 0u;
         uint32_t incl = len_r;
@@ -317,7 +324,9 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, co
             if (b0 + bytes > F.blob_cap) { F.tab.counters[KX_C_BLOB_OVERFLOW] = 1u; b0 = 0xFFFFFFFFu; }
             s_blob0 = b0;
         }
+        SF_MARK(2);
         __syncthreads();
+        SF_MARK(3);
         uint32_t row0 = s_row0, blob0 = s_blob0, more = 0;
         for (uint32_t k = 0; k < wl; k++) { row0 += s_cnt[k]; if (blob0 != 0xFFFFFFFFu) blob0 += s_bytes[k]; }
 #pragma unroll
@@ -335,6 +344,7 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, co
             const SfEntry e = q[lane];
             finalize_store_row(F, row0 + lane, e.slot, e.key, e.line, e.anchor, room ? off_r : 0u, room ? len_r : 0u);
         }
+        SF_MARK(4);
         // long lines (the rest does not end inside the 128-byte window; 19 device lines of pci.ids):
         // the whole warp takes them one at a time -- the line is staged into the (now free) name staging
         // area 32 bytes per step, then sanitised one byte per lane with ballot compaction
@@ -407,6 +417,7 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, co
             if (lane == 0) finalize_store_row(F, row0 + r, l_slot, l_key, l_line, l_anchor, ok ? at : 0u, ok ? out_len : 0u);
             __syncwarp();
         }
+        SF_MARK(5);
         // what is left of the queue moves to its front
         {
             const uint32_t rem = qn - nvalid;
@@ -420,6 +431,7 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, co
             qn = rem;
         }
         __syncthreads();  // the staging rows and the claim words are reused by the next step
+        SF_MARK(6);
         if (!more) break;
     }
 }

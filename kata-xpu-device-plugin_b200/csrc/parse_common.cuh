@@ -121,6 +121,27 @@ __device__ __forceinline__ void table_fold(const KxTableDev &tb, uint32_t key, u
     }
 }
 
+// The same fold for the callers that run on a latency chain (resolve_chunks_kernel, the small-text kernel:
+// few lines, every one of them under a FIRST anchor, so a key is hardly ever seen twice): claim first, never
+// load.  A probe step is ONE round trip (the CAS returns what the slot holds) instead of load + CAS, and a
+// warp's step count is the maximum over its lanes -- with the load the 32 folds of a warp took ~7 000 cycles.
+// The minima go out unconditionally (no return value, nobody waits for them).
+__device__ __forceinline__ void table_fold_claim(const KxTableDev &tb, uint32_t key, unsigned long long line_g,
+                                                 unsigned long long anchor_g, uint32_t &fresh_cnt) {
+    uint32_t slot = tb.cap;
+    if (key != KX_EMPTY_KEY) {
+        slot = kx_hash(key) >> tb.shift;
+        for (uint32_t step = 0;; slot = (slot + 1) & (tb.cap - 1)) {
+            const uint32_t old = atomicCAS(&tb.slots[slot].key, KX_EMPTY_KEY, key);
+            if (old == KX_EMPTY_KEY) { fresh_cnt++; break; }
+            if (old == key) break;
+            if (++step >= KX_MAX_PROBE) { tb.counters[KX_C_OVERFLOW] = 1u; return; }  // (over)full: the host grows the table
+        }
+    }
+    atomicMin(&tb.slots[slot].min_line, line_g);
+    atomicMin(&tb.slots[slot].min_anchor, anchor_g);
+}
+
 // row handle of `key` in a finished table (-1 = miss): key and row share one 8-byte load
 __device__ __forceinline__ int32_t table_probe(const KxSlot *__restrict__ slots, uint32_t cap, uint32_t shift, uint32_t key) {
     if (key == KX_EMPTY_KEY) return slots[cap].row;

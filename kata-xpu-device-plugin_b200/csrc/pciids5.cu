@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(256) resolve_ranges_kernel(const Params5 P) {
 __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Params5 P) {
     __shared__ __align__(16) uint8_t stg[RES_WARPS][STG_BYTES];
     __shared__ __align__(8) unsigned long long bars[RES_WARPS];
+    __shared__ uint16_t plist[RES_WARPS][704];  // a 2 KiB chunk holds at most 683 candidate lines ("\tX\n")
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t k7f = 0x7f7f7f7fu, k0a = 0x0a0a0a0au, k80 = 0x80808080u;
@@ -450,6 +451,7 @@ __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Pa
     const unsigned long long pol = l2_evict_first_policy();
     const uint32_t n_tasks = P.tab.counters[KX_C_DEFER];
     uint32_t par = 0, nfresh = 0;
+    const bool small_tab = P.tab.cap <= (1u << 20);
     uint32_t it = 0;
     for (uint32_t t = blockIdx.x * RES_WARPS + w; t < n_tasks; t += gridDim.x * RES_WARPS, it++) {
         // table full: the host grows it and parses again (polled every fourth task: a stale answer costs bounded probing)
@@ -478,8 +480,35 @@ __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Pa
         const uint32_t pre0 = kh[0] & ~th[0] & (th[0] ? (th[0] & (0u - th[0])) - 1u : 0xffffffffu);
         const uint32_t pre1 = kh[1] & ~th[1] & (th[1] ? (th[1] & (0u - th[1])) - 1u : 0xffffffffu);
         const unsigned long long cbase = P.base + (unsigned long long)gg * CW;
-        if ((bal0 & lt_mask) == 0u) fold_lines(P.tab, st, cbase, pre0, lane * 32u + 1u, key_hi, anchor, nfresh);
-        if (bal0 == 0u && (bal1 & lt_mask) == 0u) fold_lines(P.tab, st, cbase, pre1, (uint32_t)HALF + lane * 32u + 1u, key_hi, anchor, nfresh);
+        // The head lines become a list of line positions, folded one per lane and round: straight from the
+        // windows a lane with several short lines ran its table inserts (two dependent round trips each) in a row.
+        const uint32_t m0 = (bal0 & lt_mask) == 0u ? pre0 : 0u;
+        const uint32_t m1 = (bal0 == 0u && (bal1 & lt_mask) == 0u) ? pre1 : 0u;
+        const uint32_t mine = (uint32_t)__popc(m0) + (uint32_t)__popc(m1);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        {
+            uint32_t idx = incl - mine;
+            for (uint32_t m = m0; m; m &= m - 1u) plist[w][idx++] = (uint16_t)(lane * 32u + 1u + (uint32_t)__ffs((int)m) - 1u);
+            for (uint32_t m = m1; m; m &= m - 1u) plist[w][idx++] = (uint16_t)((uint32_t)HALF + lane * 32u + 1u + (uint32_t)__ffs((int)m) - 1u);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < total; i += 32u) {
+            const uint32_t p = plist[w][i];
+            uint32_t dv;
+            if (hex4_swar(lds32_unaligned(st + p + 1u), dv)) {
+                // L2-resident table: claim first (one round trip per probe step).  A table in DRAM: load first --
+                // measured 2.5x faster there (12.4 M keys, 1 GB table: 0.55 ms against 1.4 ms)
+                if (small_tab) table_fold_claim(P.tab, key_hi | dv, cbase + p, anchor, nfresh);
+                else table_fold(P.tab, key_hi | dv, cbase + p, anchor, nfresh);
+            }
+        }
+        __syncwarp();
         flush_fresh(P.tab, nfresh);
     }
     if (P.xa_on) {

@@ -30,6 +30,7 @@ struct SmallParams {
     const uint32_t *keys;       // join (may be null)
     size_t nq;
     int32_t *rows_out;
+    long long *trace;           // KXPU_TRACE_SMALL: [gridDim.x][8] clock64 at the phase boundaries (thread 0 of every CTA)
 };
 
 __device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t target) {
@@ -44,9 +45,17 @@ __device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t target) {
     __syncthreads();
 }
 
+constexpr int LIST_CAP = 256;              // entries of a warp's fold list (a 2 KiB chunk of pci.ids has <= 111 device lines)
+constexpr uint32_t LIST_CARRY = 0xfffu;    // governing line = the carry into the chunk
+constexpr uint32_t LIST_DEAD = 0xffeu;     // no alive governing line
+
+#define KX_SMALL_MARK(k) do { if (P.trace && threadIdx.x == 0) P.trace[blockIdx.x * 8u + (k)] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(NT, 4) small_load_kernel(const SmallParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    KX_SMALL_MARK(0);
     __shared__ __align__(8) unsigned long long bars[WARPS];
+    __shared__ uint32_t s_list[WARPS][LIST_CAP];
     const KxTableDev &tab = P.F.tab;
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -123,16 +132,22 @@ __global__ void __launch_bounds__(NT, 4) small_load_kernel(const SmallParams P) 
         if (n_rel > (uint32_t)CW && __reduce_or_sync(0xffffffffu, rawnl) == 0u && lane == 0)
             atomicOr(&tab.counters[KX_C_LONGLINE_HINT], 1u);  // 2 KiB without a newline: maybe a >= 64 KiB line
     }
+    KX_SMALL_MARK(1);
     grid_barrier(&tab.counters[KX_C_GRIDBAR], gridDim.x);
+    KX_SMALL_MARK(2);
 
     // ---------------------------------------------------------------- phase 2
     uint32_t nfresh = 0;
     if (have) {
+        const long long w_t0 = P.trace ? clock64() : 0;
+        long long w_t1 = 0;
+        uint32_t lb_iters = 0;
         // governing line at the start of the chunk: nearest published prefix in front of it
         unsigned long long carry = 0;
         if (g > 0u) {
             long long q0 = (long long)g - 1;
             for (;;) {
+                lb_iters++;
                 const long long q = q0 - lane;
                 const unsigned long long sv = q >= 0 ? P.state[q] : ST_NONE;
                 const uint32_t m = __ballot_sync(0xffffffffu, (sv & ST_MASK) == ST_PREFIX);
@@ -143,25 +158,20 @@ __global__ void __launch_bounds__(NT, 4) small_load_kernel(const SmallParams P) 
                 q0 -= 32;  // chunk 0 always publishes a prefix: the loop ends there at the latest
             }
         }
-        // my windows' top-level lines, in order: the device lines behind an ALIVE one (its offset is the
-        // final vendor_first of its id) are folded; linfo = last top-level line of the window
-        uint32_t linfo[2] = {P_NONE, P_NONE};
+        // my windows' top-level lines: alive iff the line is the FIRST of its vendor id (its offset is the final
+        // vendor_first); linfo = last top-level line of the window
+        uint32_t linfo[2] = {P_NONE, P_NONE}, at[2] = {0u, 0u};
         for (int h = 0; h < 2; h++) {
             uint32_t t = th[h];
             const uint32_t pbase = (uint32_t)h * HALF + lane * 32u + 1u;
             while (t) {
                 const uint32_t bit = t & (0u - t);
-                const uint32_t rest = t ^ bit;
-                t = rest;
+                t ^= bit;
                 const uint32_t p = pbase + (31u - (uint32_t)__clz((int)bit));
                 uint32_t val;
                 const bool ok = hex4_swar(lds32_unaligned(st + p), val);
                 const bool alive = ok && cbase + p == tab.vendor_first[val];
-                if (alive) {
-                    const uint32_t nxt = rest & (0u - rest);
-                    const uint32_t seg = (kh[h] & ~th[h]) & ~(bit | (bit - 1u)) & (nxt ? nxt - 1u : 0xffffffffu);
-                    fold_lines(tab, st, cbase, seg, pbase, val << 16, cbase + p, nfresh);
-                }
+                if (alive) at[h] |= bit;
                 linfo[h] = (alive ? 0x80000000u : 0u) | ((ok ? val : 0u) << 15) | p;
             }
         }
@@ -169,43 +179,108 @@ __global__ void __launch_bounds__(NT, 4) small_load_kernel(const SmallParams P) 
             base_info = (base_info & 0x7fffffffu) | (((base_info >> 31) && tab.vendor_first[(base_info >> 15) & 0xffffu] == 0ull) ? 0x80000000u : 0u);
         // device lines in front of a window's first top-level line: governed by the last top-level line of
         // an earlier window of this chunk, else by the carry
-        const uint32_t pre0 = kh[0] & ~th[0] & (th[0] ? (th[0] & (0u - th[0])) - 1u : 0xffffffffu);
-        const uint32_t pre1 = kh[1] & ~th[1] & (th[1] ? (th[1] & (0u - th[1])) - 1u : 0xffffffffu);
         const uint32_t bal0 = __ballot_sync(0xffffffffu, th[0] != 0u), bal1 = __ballot_sync(0xffffffffu, th[1] != 0u);
         const uint32_t s0 = bal0 & lt_mask, s1 = bal1 & lt_mask;
         const uint32_t x0 = __shfl_sync(0xffffffffu, linfo[0], s0 ? 31 - __clz((int)s0) : 0);
         const uint32_t l0 = __shfl_sync(0xffffffffu, linfo[0], bal0 ? 31 - __clz((int)bal0) : 0);
         const uint32_t x1 = __shfl_sync(0xffffffffu, linfo[1], s1 ? 31 - __clz((int)s1) : 0);
         const uint32_t last0 = bal0 ? l0 : base_info;
-        const uint32_t cin0 = s0 ? x0 : base_info;
-        const uint32_t cin1 = s1 ? x1 : last0;
-        if (cin0 != P_NONE && (cin0 >> 31))
-            fold_lines(tab, st, cbase, pre0, lane * 32u + 1u, ((cin0 >> 15) & 0xffffu) << 16, cbase + (cin0 & 0x7fffu), nfresh);
-        if (cin1 != P_NONE && (cin1 >> 31))
-            fold_lines(tab, st, cbase, pre1, (uint32_t)HALF + lane * 32u + 1u, ((cin1 >> 15) & 0xffffu) << 16, cbase + (cin1 & 0x7fffu), nfresh);
-        // head lines (no top-level line of this chunk in front of them): the carry governs them
-        const uint32_t hw0 = cin0 == P_NONE ? pre0 : 0u, hw1 = cin1 == P_NONE ? pre1 : 0u;
-        if ((carry & CV_HAS_TOP) && (carry & CV_VOK)) {
-            const uint32_t cv = (uint32_t)(carry >> 44) & 0xffffu;
-            const unsigned long long anchor = carry & CV_ANCHOR_MASK;
-            if (tab.vendor_first[cv] == anchor) {
-                fold_lines(tab, st, cbase, hw0, lane * 32u + 1u, cv << 16, anchor, nfresh);
-                fold_lines(tab, st, cbase, hw1, (uint32_t)HALF + lane * 32u + 1u, cv << 16, anchor, nfresh);
+        const uint32_t cin[2] = {s0 ? x0 : base_info, s1 ? x1 : last0};
+        const uint32_t cv = (uint32_t)(carry >> 44) & 0xffffu;
+        const unsigned long long canchor = carry & CV_ANCHOR_MASK;
+        const bool carry_alive = (carry & CV_HAS_TOP) && (carry & CV_VOK) && tab.vendor_first[cv] == canchor;
+        // Every device line under an alive governing line becomes one entry (line position | position of the
+        // governing line << 12, LIST_CARRY = the carry) of the warp's list; the list is then folded one entry
+        // per lane and round.  Folding straight from the windows left the table inserts -- two dependent L2
+        // round trips each -- serialised per lane: ~10 in a row for a chunk of short lines (18 us of 53).
+        auto gov_in = [&](int h) -> uint32_t {  // governing line in front of window h
+            return cin[h] == P_NONE ? (carry_alive ? LIST_CARRY : LIST_DEAD) : ((cin[h] >> 31) ? (cin[h] & 0x7fffu) : LIST_DEAD);
+        };
+        uint32_t mine = 0;
+        for (int h = 0; h < 2; h++) {
+            // lines in front of the window's first top-level line count iff gov_in is alive, those behind an alive top always
+            const uint32_t dl = kh[h] & ~th[h];
+            const uint32_t first = th[h] & (0u - th[h]);
+            const uint32_t pre = dl & (first ? first - 1u : 0xffffffffu);
+            if (gov_in(h) != LIST_DEAD) mine += (uint32_t)__popc(pre);
+            uint32_t t = th[h];
+            while (t) {
+                const uint32_t bit = t & (0u - t);
+                t ^= bit;
+                const uint32_t nxt = t & (0u - t);
+                if (at[h] & bit) mine += (uint32_t)__popc(dl & ~(bit | (bit - 1u)) & (nxt ? nxt - 1u : 0xffffffffu));
             }
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t off = incl - mine;
+        uint32_t *list = s_list[w];
+        if (P.trace) w_t1 = clock64();
+        for (uint32_t base = 0; base < total; base += (uint32_t)LIST_CAP) {  // one pass unless the chunk has > LIST_CAP lines
+            // my entries whose list index falls into [base, base + LIST_CAP)
+            {
+                uint32_t idx = off;
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t pbase = (uint32_t)h * HALF + lane * 32u + 1u;
+                    uint32_t gov = gov_in(h);
+                    uint32_t m = kh[h];
+                    while (m) {
+                        const uint32_t bit = m & (0u - m);
+                        m ^= bit;
+                        const uint32_t p = pbase + (31u - (uint32_t)__clz((int)bit));
+                        if (th[h] & bit) {
+                            gov = (at[h] & bit) ? p : LIST_DEAD;
+                        } else if (gov != LIST_DEAD) {
+                            if (idx >= base && idx < base + (uint32_t)LIST_CAP) list[idx - base] = p | (gov << 12);
+                            idx++;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            const uint32_t cnt = total - base < (uint32_t)LIST_CAP ? total - base : (uint32_t)LIST_CAP;
+            for (uint32_t i = lane; i < cnt; i += 32u) {
+                const uint32_t e = list[i];
+                const uint32_t p = e & 0xfffu, gp = e >> 12;
+                uint32_t key_hi = cv << 16, dv;
+                unsigned long long anchor = canchor;
+                if (gp != LIST_CARRY) {
+                    uint32_t val;
+                    hex4_swar(lds32_unaligned(st + gp), val);  // an alive line: its id parsed fine before
+                    key_hi = val << 16;
+                    anchor = cbase + gp;
+                }
+                if (hex4_swar(lds32_unaligned(st + p + 1u), dv)) table_fold_claim(tab, key_hi | dv, cbase + p, anchor, nfresh);
+            }
+            __syncwarp();
+        }
+        if (P.trace && lane == 0) {
+            long long *tw = P.trace + (size_t)gridDim.x * 8u + (size_t)g * 4u;
+            tw[0] = clock64() - w_t0; tw[1] = w_t1 - w_t0; tw[2] = total; tw[3] = lb_iters;
         }
     }
     flush_fresh(tab, nfresh);
+    KX_SMALL_MARK(3);
     grid_barrier(&tab.counters[KX_C_GRIDBAR], 2u * gridDim.x);
+    KX_SMALL_MARK(4);
 
     // ---------------------------------------------------------------- phase 3
-    select_finalize_body(P.F, 8u);
+    select_finalize_body(P.F, P.F.scan_w);
+    KX_SMALL_MARK(5);
     if (P.nq == 0) return;
     grid_barrier(&tab.counters[KX_C_GRIDBAR], 3u * gridDim.x);
+    KX_SMALL_MARK(6);
 
     // ---------------------------------------------------------------- phase 4
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.nq; i += stride)
         P.rows_out[i] = table_probe(tab.slots, tab.cap, tab.shift, P.keys[i]);
+    KX_SMALL_MARK(7);
 }
 
 }  // namespace kxsmall

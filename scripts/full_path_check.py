@@ -15,13 +15,18 @@ for nv, nd in [(int(x) for x in s.split("x")) for s in os.environ.get("SIZES", "
     n = len(text)
     d = kx.dev_alloc(n)
     kx.upload(d, text)
-    for it in range(5):
+    ITERS = int(os.environ.get("ITERS", "5"))
+    for it in range(ITERS):
         tb = kx.pciids_load_device(d, n)
         tm = kx.timings()
         print("%dx%d iter %d: %d B, %d rows | parse %.3f ms (%.1f GB/s) resolve %.3f ms finalize %.3f ms" %
               (nv, nd, it, n, tb.rows, tm[B.T_PARSE], n / tm[B.T_PARSE] / 1e6, tm[B.T_RESOLVE], tm[B.T_FINALIZE]), flush=True)
-        if it < 4:
+        if it < ITERS - 1:
             tb.free()
+    if os.environ.get("NO_ORACLE"):
+        tb.free()
+        kx.dev_free(d)
+        continue
     keys, offs, rows = kx.table_export(tb)
     t0 = time.time()
     orows = O.table_build(text)
