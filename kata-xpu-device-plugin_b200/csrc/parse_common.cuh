@@ -121,25 +121,40 @@ __device__ __forceinline__ void table_fold(const KxTableDev &tb, uint32_t key, u
     }
 }
 
-// The same fold for the callers that run on a latency chain (resolve_chunks_kernel, the small-text kernel:
-// few lines, every one of them under a FIRST anchor, so a key is hardly ever seen twice): claim first, never
-// load.  A probe step is ONE round trip (the CAS returns what the slot holds) instead of load + CAS, and a
-// warp's step count is the maximum over its lanes -- with the load the 32 folds of a warp took ~7 000 cycles.
-// The minima go out unconditionally (no return value, nobody waits for them).
-__device__ __forceinline__ void table_fold_claim(const KxTableDev &tb, uint32_t key, unsigned long long line_g,
-                                                 unsigned long long anchor_g, uint32_t &fresh_cnt) {
-    uint32_t slot = tb.cap;
-    if (key != KX_EMPTY_KEY) {
-        slot = kx_hash(key) >> tb.shift;
-        for (uint32_t step = 0;; slot = (slot + 1) & (tb.cap - 1)) {
-            const uint32_t old = atomicCAS(&tb.slots[slot].key, KX_EMPTY_KEY, key);
-            if (old == KX_EMPTY_KEY) { fresh_cnt++; break; }
-            if (old == key) break;
-            if (++step >= KX_MAX_PROBE) { tb.counters[KX_C_OVERFLOW] = 1u; return; }  // (over)full: the host grows the table
+// The fold for the callers that run on a latency chain (resolve_chunks_kernel, the small-text kernel: few
+// lines, every one of them under a FIRST anchor, so a key is hardly ever seen twice): claim first, never load.
+// A probe step is ONE round trip (the CAS returns what the slot holds) instead of load + CAS, and a warp's step
+// count is the maximum over its lanes -- with the load the 32 folds of a warp took ~7 000 cycles.  The minima
+// go out unconditionally (no return value, nobody waits for them).  Two folds per lane (on1: the second one
+// exists), their probe steps in flight together.
+__device__ __forceinline__ void table_fold_claim2(const KxTableDev &tb, uint32_t key0, unsigned long long line0, unsigned long long anchor0,
+                                                  bool on1, uint32_t key1, unsigned long long line1, unsigned long long anchor1,
+                                                  uint32_t &fresh_cnt) {
+    uint32_t slot0 = key0 == KX_EMPTY_KEY ? tb.cap : (kx_hash(key0) >> tb.shift);
+    uint32_t slot1 = key1 == KX_EMPTY_KEY ? tb.cap : (kx_hash(key1) >> tb.shift);
+    bool open0 = key0 != KX_EMPTY_KEY, open1 = on1 && key1 != KX_EMPTY_KEY, ok0 = true, ok1 = on1;
+    for (uint32_t step = 0; open0 || open1; step++) {
+        uint32_t old0 = 0, old1 = 0;
+        if (open0) old0 = atomicCAS(&tb.slots[slot0].key, KX_EMPTY_KEY, key0);
+        if (open1) old1 = atomicCAS(&tb.slots[slot1].key, KX_EMPTY_KEY, key1);
+        if (open0) {
+            if (old0 == KX_EMPTY_KEY) { fresh_cnt++; open0 = false; }
+            else if (old0 == key0) open0 = false;
+            else slot0 = (slot0 + 1) & (tb.cap - 1);
+        }
+        if (open1) {
+            if (old1 == KX_EMPTY_KEY) { fresh_cnt++; open1 = false; }
+            else if (old1 == key1) open1 = false;
+            else slot1 = (slot1 + 1) & (tb.cap - 1);
+        }
+        if (step + 1 >= KX_MAX_PROBE && (open0 || open1)) {  // (over)full: the host grows the table
+            tb.counters[KX_C_OVERFLOW] = 1u;
+            ok0 = ok0 && !open0; ok1 = ok1 && !open1;
+            break;
         }
     }
-    atomicMin(&tb.slots[slot].min_line, line_g);
-    atomicMin(&tb.slots[slot].min_anchor, anchor_g);
+    if (ok0) { atomicMin(&tb.slots[slot0].min_line, line0); atomicMin(&tb.slots[slot0].min_anchor, anchor0); }
+    if (ok1) { atomicMin(&tb.slots[slot1].min_line, line1); atomicMin(&tb.slots[slot1].min_anchor, anchor1); }
 }
 
 // row handle of `key` in a finished table (-1 = miss): key and row share one 8-byte load

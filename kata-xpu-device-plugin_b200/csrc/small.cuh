@@ -244,18 +244,29 @@ __global__ void __launch_bounds__(NT, 4) small_load_kernel(const SmallParams P) 
             }
             __syncwarp();
             const uint32_t cnt = total - base < (uint32_t)LIST_CAP ? total - base : (uint32_t)LIST_CAP;
-            for (uint32_t i = lane; i < cnt; i += 32u) {
-                const uint32_t e = list[i];
+            // two entries per lane and round, their probe steps in flight together
+            auto entry = [&](uint32_t e, uint32_t &key, unsigned long long &line, unsigned long long &anchor) -> bool {
                 const uint32_t p = e & 0xfffu, gp = e >> 12;
                 uint32_t key_hi = cv << 16, dv;
-                unsigned long long anchor = canchor;
+                anchor = canchor;
                 if (gp != LIST_CARRY) {
                     uint32_t val;
                     hex4_swar(lds32_unaligned(st + gp), val);  // an alive line: its id parsed fine before
                     key_hi = val << 16;
                     anchor = cbase + gp;
                 }
-                if (hex4_swar(lds32_unaligned(st + p + 1u), dv)) table_fold_claim(tab, key_hi | dv, cbase + p, anchor, nfresh);
+                line = cbase + p;
+                const bool ok = hex4_swar(lds32_unaligned(st + p + 1u), dv);
+                key = key_hi | dv;
+                return ok;
+            };
+            for (uint32_t i = lane; i < cnt; i += 64u) {
+                uint32_t k0, k1 = 0;
+                unsigned long long l0, a0, l1 = 0, a1 = 0;
+                bool v0 = entry(list[i], k0, l0, a0);
+                bool v1 = i + 32u < cnt && entry(list[i + 32u], k1, l1, a1);
+                if (!v0 && v1) { k0 = k1; l0 = l1; a0 = a1; v0 = true; v1 = false; }
+                if (v0) table_fold_claim2(tab, k0, l0, a0, v1, k1, l1, a1, nfresh);
             }
             __syncwarp();
         }
