@@ -73,6 +73,7 @@ int32_t kx_ctx_create_on(int32_t ordinal, kxpu_ctx **out) {
     const char *fr = getenv("KXPU_RCH");
     c->force_rch = (fr && fr[0] >= '1' && fr[0] <= '8' && !fr[1]) ? fr[0] - '0' : 0;
     c->no_small = getenv("KXPU_NO_SMALL") != nullptr;
+    c->no_zero_copy = getenv("KXPU_NO_ZERO_COPY") != nullptr;
     if (const char *sw = getenv("KXPU_SCAN_W")) { const int v = atoi(sw); c->force_scan_w = (v == 8 || v == 16 || v == 32) ? v : 0; }
     *out = c;
     return KXPU_OK;
@@ -468,7 +469,18 @@ struct KxJoin {  // optional batched join enqueued behind the finalize, in front
     size_t n;
     int32_t *d_rows;
     int32_t *h_rows;  // optional: the row handles also go to this host buffer (inside the one round trip)
+    // zero-copy ingest of a small text: the text sits in mapped pinned host memory (device address), d_keys / d_rows
+    // are mapped host buffers too; the small-text kernel reads / writes them over PCIe, no copy is enqueued
+    const uint8_t *src_text;
 };
+
+// device address of `p` if it points into mapped pinned host memory, else nullptr
+static void *kx_mapped_host(const void *p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
 
 // chunks the cooperative small-text kernel can take: one per warp of a grid that is resident at once
 // (KXPU_NO_SMALL=1, read when the ctx is created, sends small texts through the big-text kernels: tests)
@@ -500,6 +512,7 @@ static int32_t launch_small(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text,
     F.row_name_off = t->row_name_off; F.row_name_len = t->row_name_len;
     F.blob = t->blob; F.blob_cap = t->blob_cap;
     if (join) { P.keys = join->d_keys; P.nq = join->n; P.rows_out = join->d_rows; }
+    if (join && join->src_text) { P.text_src = join->src_text; P.h_ctl = ctx->h_ctl; }
     void *args[] = {&P};
     // the whole resident grid: phases 1 / 2 use one warp per chunk, the names and the join every warp
     const unsigned grid = std::max<unsigned>((P.num_chunks + WARPS - 1) / WARPS, (unsigned)(ctx->small_chunks / WARPS));
@@ -586,10 +599,13 @@ static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t 
         kxpu_table *t = nullptr;
         int32_t rc = kx_table_acquire(ctx, cap, blob_cap, num_chunks, &t);
         if (rc != KXPU_OK) return rc;
-        if (num_chunks > 0 && num_chunks <= small_text_chunks(ctx) && !have_trunc) {
+        const bool small_path = num_chunks > 0 && num_chunks <= small_text_chunks(ctx) && !have_trunc;
+        if (small_path) {
             // a small text (the real pci.ids): parse, fold, names and join in ONE cooperative launch
             rc = launch_small(ctx, t, d_text, n, join);
         } else {
+            // zero-copy call that cannot take the small-text kernel (any more): the text comes over with a plain copy
+            if (join && join->src_text && attempt == 0) cudaMemcpyAsync(const_cast<uint8_t *>(d_text), join->src_text, n, cudaMemcpyDefault, ctx->stream);
             rc = kx_launch_parse(ctx, t, d_text, n, 0, 0, nullptr);
             // a text with a >= 2 KiB stretch without a newline was seen on an earlier attempt: the exact
             // bufio.ErrTooLong cut-off is computed before the finalize
@@ -600,8 +616,11 @@ static int32_t kx_build_table_join(kxpu_ctx *ctx, const uint8_t *d_text, size_t 
             if (rc == KXPU_OK && join) rc = kx_launch_lookup(ctx, t, join->d_keys, join->n, join->d_rows);
         }
         if (rc != KXPU_OK) { kx_table_release(ctx, t); return rc; }
-        if (join && join->h_rows && join->n) cudaMemcpyAsync(join->h_rows, join->d_rows, join->n * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        const bool zero_copy = small_path && join && join->src_text;  // the kernel wrote rows and counters to host memory itself
+        if (!zero_copy) {
+            if (join && join->h_rows && join->n) cudaMemcpyAsync(join->h_rows, join->d_rows, join->n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(ctx->h_ctl, t->dev.counters, KX_C_COUNT * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        }
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             KX_SET_ERR(ctx, "parse/finalize failed: %s", cudaGetErrorString(e));
@@ -646,7 +665,7 @@ extern "C" int32_t kxpu_pciids_join_device(kxpu_ctx *ctx, const void *d_text, si
     KX_ENTER(ctx);
     if (!out || (!d_text && n) || (nq && (!d_keys || !d_rows_out))) return KXPU_E_INVALID;
     kx_clear_timings(ctx);
-    const KxJoin j{d_keys, nq, d_rows_out, nullptr};
+    const KxJoin j{d_keys, nq, d_rows_out, nullptr, nullptr};
     return kx_build_table_join(ctx, (const uint8_t *)d_text, n, out, &j);
 }
 
@@ -694,13 +713,27 @@ extern "C" int32_t kxpu_pciids_join(kxpu_ctx *ctx, const uint8_t *text, size_t n
     int32_t rc = stage_reserve(ctx, o_rows + nq * 4 + 16);
     if (rc != KXPU_OK) return rc;
     uint8_t *d = (uint8_t *)ctx->d_stage;
+    // Small text in mapped pinned host memory (cudaHostAlloc / cudaHostRegister; what a host that reads /usr/pci.ids
+    // into a pinned buffer passes): no copy at all.  The cooperative kernel pulls the text over PCIe in its first
+    // phase (one TMA bulk copy per 2 KiB chunk, all in flight at once), reads the keys and writes the row handles and
+    // the table counters straight to host memory; the call is one launch and one stream synchronisation.
+    const uint32_t chunks = (uint32_t)((n + kxparse::CW - 1) / kxparse::CW);
+    if (nq && chunks > 0 && chunks <= small_text_chunks(ctx) && !ctx->no_zero_copy) {
+        const uint8_t *m_text = (const uint8_t *)kx_mapped_host(text);
+        const uint32_t *m_keys = (const uint32_t *)kx_mapped_host(keys);
+        int32_t *m_rows = (int32_t *)kx_mapped_host(rows_out);
+        if (m_text && m_keys && m_rows && (reinterpret_cast<uintptr_t>(m_text) & 15u) == 0) {
+            const KxJoin j{m_keys, nq, m_rows, nullptr, m_text};
+            return kx_build_table_join(ctx, d, n, out, &j);
+        }
+    }
     cudaError_t e = cudaMemcpyAsync(d, text, n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && nq) e = cudaMemcpyAsync(d + o_keys, keys, nq * 4, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) {
         KX_SET_ERR(ctx, "H2D copy of the text / keys failed: %s", cudaGetErrorString(e));
         return KXPU_E_CUDA;
     }
-    const KxJoin j{(const uint32_t *)(d + o_keys), nq, (int32_t *)(d + o_rows), rows_out};
+    const KxJoin j{(const uint32_t *)(d + o_keys), nq, (int32_t *)(d + o_rows), rows_out, nullptr};
     return kx_build_table_join(ctx, d, n, out, &j);
 }
 

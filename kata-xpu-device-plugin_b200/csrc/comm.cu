@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(256) xb_push_kernel(const XbParams P) {
     uint32_t st = 0;
     if (P.counters[KX_C_BLOB_OVERFLOW] || n_sel > P.rows_cap || blob_used > P.blob_cap) st |= XS_SLAB_OVERFLOW;
     const int q = (int)blockIdx.y;
-    if (!st && q != P.self) {
+    const bool pushes = !st && q != P.self && (n_sel != 0u || blob_used != 0u);
+    if (pushes) {
         const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
         uint8_t *dst = P.tg.region[q] + P.o_slab;
         const size_t r16 = (size_t)n_sel * (sizeof(SlabRow) / 16);
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(256) xb_push_kernel(const XbParams P) {
     // (cumulative) fence orders them in front of the counter and, in the last CTA, of the flags
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        if (pushes) __threadfence_system();
         const uint32_t prev = atomicAdd(P.done, 1u);
         if (prev == gridDim.x * gridDim.y - 1u) {
             *P.done = 0u;
@@ -194,7 +195,6 @@ __global__ void __launch_bounds__(256) xb_push_kernel(const XbParams P) {
             __threadfence_system();
             if (P.raise_flags)
                 for (int k = 0; k < P.tg.n; k++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[k] + P.o_flag) = P.epoch;
-            __threadfence_system();
         }
     }
 }
@@ -297,10 +297,19 @@ __global__ void __launch_bounds__(256) join_gather_kernel(const JoinParams P) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     for (size_t b0 = (size_t)blockIdx.x * JOIN_PER_CTA; b0 < P.n; b0 += (size_t)gridDim.x * JOIN_PER_CTA) {
         const uint32_t cnt = P.n - b0 < (size_t)JOIN_PER_CTA ? (uint32_t)(P.n - b0) : (uint32_t)JOIN_PER_CTA;
+        {
+            static_assert(JOIN_PER_CTA == 4 * 256, "four keys per thread");
+            uint32_t key[4] = {0u, 0u, 0u, 0u}, on = 0;
+            int32_t row[4];
 #pragma unroll
-        for (int k = 0; k < JOIN_PER_CTA / 256; k++) {
-            const uint32_t j = tid + 256u * k;
-            if (j < cnt) res[j] = kxparse::table_probe(P.slots, P.cap, P.shift, P.keys[b0 + j]);
+            for (int k = 0; k < 4; k++) {
+                const uint32_t j = tid + 256u * k;
+                if (j < cnt) { key[k] = P.keys[b0 + j]; on |= 1u << k; }
+            }
+            kxparse::table_probe4(P.slots, P.cap, P.shift, key, on, row);  // the four probes of a thread run side by side
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if ((on >> k) & 1u) res[tid + 256u * k] = row[k];
         }
         __syncthreads();
         const size_t o = P.key_offset + b0;
@@ -324,7 +333,6 @@ __global__ void __launch_bounds__(256) join_gather_kernel(const JoinParams P) {
             __threadfence_system();
             if (P.raise_flags)
                 for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[q] + P.o_flag) = P.epoch;
-            __threadfence_system();
         }
     }
 }

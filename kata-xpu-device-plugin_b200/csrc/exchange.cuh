@@ -104,7 +104,6 @@ __device__ __forceinline__ void xa_finish(const XaParams &P) {
     __threadfence_system();
     if (P.raise_flags)
         for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[q] + P.o_flag) = P.epoch;
-    __threadfence_system();
 }
 
 // Flags of one phase: lane q of the calling warp waits for rank q's flag of this epoch (~4 s time-out).

@@ -170,6 +170,31 @@ __device__ __forceinline__ int32_t table_probe(const KxSlot *__restrict__ slots,
     return -1;
 }
 
+// four keys at once: the probe loads of a step are in flight together (a probe is one L2 round trip; used where
+// a thread has several keys anyway -- with one key per thread and the grid in several waves the plain probe is as fast)
+__device__ __forceinline__ void table_probe4(const KxSlot *__restrict__ slots, uint32_t cap, uint32_t shift, const uint32_t (&key)[4],
+                                             uint32_t on, int32_t (&row)[4]) {
+    uint32_t slot[4], open = on & 0xfu;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        row[j] = -1;
+        slot[j] = key[j] == KX_EMPTY_KEY ? cap : (kx_hash(key[j]) >> shift);
+    }
+    for (uint32_t step = 0; open && step < cap; step++) {
+        uint2 kr[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((open >> j) & 1u) kr[j] = __ldg(reinterpret_cast<const uint2 *>(&slots[slot[j]]));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (!((open >> j) & 1u)) continue;
+            if (slot[j] == cap || kr[j].x == key[j]) { row[j] = (int32_t)kr[j].y; open &= ~(1u << j); }
+            else if (kr[j].x == KX_EMPTY_KEY) open &= ~(1u << j);
+            else slot[j] = (slot[j] + 1) & (cap - 1);
+        }
+    }
+}
+
 // find or claim the slot of `key` while the table is being built (0xffffffff: table full);
 // fresh_cnt as in table_fold
 __device__ __forceinline__ uint32_t table_claim(const KxTableDev &tb, uint32_t key, uint32_t &fresh_cnt) {

@@ -30,6 +30,9 @@ struct SmallParams {
     const uint32_t *keys;       // join (may be null)
     size_t nq;
     int32_t *rows_out;
+    const uint8_t *text_src;    // zero-copy ingest: the text in mapped pinned HOST memory (phase 1 reads it over PCIe and leaves a
+                                // device copy in `text` for the later phases); nullptr: `text` already is the device copy
+    uint32_t *h_ctl;            // zero-copy: the table counters go straight to this mapped host buffer (after the names phase)
     long long *trace;           // KXPU_TRACE_SMALL: [gridDim.x][8] clock64 at the phase boundaries (thread 0 of every CTA)
 };
 
@@ -70,19 +73,30 @@ __global__ void __launch_bounds__(NT, 4) small_load_kernel(const SmallParams P) 
     uint32_t n_rel = CW + 1, nl[2] = {0, 0}, th[2] = {0, 0}, kh[2] = {0, 0}, rawnl = 0;
     uint32_t base_info = P_NONE;  // top-level line at offset 0 of the text (no newline in front of it)
     if (have) {
+        const uint8_t *src = P.text_src ? P.text_src : P.text;
         if (g < P.tma_limit) {
             const uint32_t bar = smem_u32(&bars[w]);
             if (lane == 0) {
                 mbar_init(&bars[w], 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
                 mbar_expect_tx_a(bar, STG_BYTES);
-                tma_load_a(st, P.text + cbase, STG_BYTES, bar, l2_evict_first_policy());
+                tma_load_a(st, src + cbase, STG_BYTES, bar, l2_evict_first_policy());
             }
             __syncwarp();
             while (!mbar_try_a(bar, 0)) {
             }
         } else {
-            n_rel = stage_chunk_manual(P.text, P.n, g, lane, stage);
+            n_rel = stage_chunk_manual(src, P.n, g, lane, stage);
+        }
+        if (P.text_src) {
+            // zero-copy ingest: the chunk came over PCIe; its 2 KiB go to the device copy the names phase reads
+            // (the copy has 16 bytes of slack behind n; bytes behind the text are zero in the stage)
+            uint8_t *dcopy = const_cast<uint8_t *>(P.text) + cbase;
+#pragma unroll
+            for (int k = 0; k < CW / 16 / 32; k++) {
+                const uint32_t cc = lane + 32u * (uint32_t)k;
+                if (cbase + 16ull * cc < P.n) *reinterpret_cast<uint4 *>(dcopy + 16u * cc) = *reinterpret_cast<const uint4 *>(stage + 16u * cc);
+            }
         }
         nl_masks(st, lane, n_rel, k7f, k0a, k80, nl, rawnl);
         tops_of2(st + lane * 32u + 1u, nl[0], nl[1], th[0], th[1]);
@@ -286,6 +300,7 @@ __global__ void __launch_bounds__(NT, 4) small_load_kernel(const SmallParams P) 
     if (P.nq == 0) return;
     grid_barrier(&tab.counters[KX_C_GRIDBAR], 3u * gridDim.x);
     KX_SMALL_MARK(6);
+    if (P.h_ctl && blockIdx.x == 0 && threadIdx.x < KX_C_COUNT) P.h_ctl[threadIdx.x] = __ldcg(&tab.counters[threadIdx.x]);  // final since the barrier
 
     // ---------------------------------------------------------------- phase 4
     const size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -410,6 +410,43 @@ def test_host_join_one_round_trip(kx, oracle, pci_text, oracle_rows, workloads):
     tab.free()
 
 
+def test_zero_copy_join_from_pinned_host_buffers(kx, oracle, pci_text, oracle_rows, workloads):
+    """kxpu_pciids_join with text, keys and rows in mapped pinned host memory: the small-text kernel pulls the text
+    over PCIe itself (no copy is enqueued) and writes row handles and counters to host memory.  Same results as
+    the copying path for the real file, ragged sizes around chunk boundaries, edge texts, a text whose table has to
+    grow (retry) and a text with a >= 64 KiB line (second attempt leaves the small-text kernel)."""
+    rng = np.random.default_rng(11)
+    texts = [pci_text] + [pci_text[:n] for n in (1, 15, 16, 17, 2047, 2048, 2049, 2064, 4096, 4097, 300001)] + list(EDGE_TEXTS)
+    texts.append(_big_random_text(rng, 60000, 200, 0.2))                     # > 32 k keys: the 2^16 table grows (retry)
+    texts.append(b"10de  NVIDIA\n\t2330  H100\n" + b"x" * 70000 + b"\n\t2331  Other\n10df  Next\n\t0001  Dev\n")  # ErrTooLong cut-off
+    for text in texts:
+        if len(text) == 0:
+            continue
+        want = oracle.table_build(text)
+        q = workloads.make_queries(want["key"] if len(want["key"]) else np.array([0x10de2330], np.uint32), 777, 5)
+        h_text, p1 = kx.pinned(len(text))
+        h_text[:] = np.frombuffer(text, np.uint8)
+        h_q, p2 = kx.pinned(len(q) * 4, np.uint32)
+        h_q[:] = q
+        h_r, p3 = kx.pinned(len(q) * 4, np.int32)
+        h_r[:] = -7
+        try:
+            tab, rows = kx.pciids_join(h_text, h_q, rows_out=h_r)
+            keys, offs, _ = kx.table_export(tab)
+            assert np.array_equal(keys, want["key"]) and np.array_equal(offs, want["line_off"]), len(text)
+            assert np.array_equal(rows, kx.lookup(tab, q)), len(text)
+            ref_tab, ref_rows = kx.pciids_join(bytes(text), q)          # pageable buffers: the copying path
+            assert tab.rows == ref_tab.rows
+            names, _, _ = kx.names(tab, rows[:200])
+            ref_names, _, _ = kx.names(ref_tab, ref_rows[:200])
+            assert names == ref_names
+            tab.free()
+            ref_tab.free()
+        finally:
+            for p in (p1, p2, p3):
+                kx.pinned_free(p)
+
+
 def test_small_texts_through_the_big_text_kernels(oracle, pci_text, monkeypatch):
     """Small texts normally take the cooperative one-launch kernel; KXPU_NO_SMALL=1 sends them through
     parse_kernel_v5 + resolve + select_finalize, which must agree (ragged sizes, edge texts, real file)."""
