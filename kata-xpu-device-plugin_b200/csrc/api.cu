@@ -437,6 +437,7 @@ int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, 
     if (slab) {
         F.slab_rows = reinterpret_cast<kxx::SlabRow *>(slab->rows); F.slab_rows_cap = slab->rows_cap;
         F.blob = slab->blob; F.blob_cap = slab->blob_cap;
+        F.tail = slab->tail;
     }
     KxTimer tm(ctx, KXPU_T_FINALIZE);
     // validity + names: a warp scans scan_w table slots per step, persistent grid.  Small tables: 8 slots per

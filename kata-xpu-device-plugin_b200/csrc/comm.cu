@@ -14,15 +14,18 @@
 //      global first anchor of every vendor id (min over the R blocks), so a row is a WINNER iff
 //      its anchor equals it -- and winners are globally unique per key (the first block sits in
 //      exactly one shard).
-//   B  winners only: each rank sanitises the names of its winner rows and pushes rows + names
-//      into its slab in every rank's region.  Shards that hold no first block push nothing.
-//      Every rank then inserts the winners of all ranks into the table it parsed into -- no
-//      second table, no min-merge, row handles are global (rank prefix + index).
+//   B  winners only, as a PULL: each rank sanitises the names of its winner rows straight into its own slab
+//      (finalize kernel); the last CTA of that kernel writes the slab header and raises "slab ready" on every
+//      rank.  Shards that hold no first block publish an empty slab.  Every rank's merge kernel then reads the
+//      slabs of all ranks over NVLink (uncached loads) and inserts the winners into the table it parsed into
+//      -- no second table, no min-merge, row handles are global (rank prefix + index).  (Until round 2 a push
+//      kernel copied the slab into every peer: the same step time -- the cost is the fence + flag latency at
+//      the phase boundary, not the copy -- but one kernel and R slab copies more.)
 //   C  (join) every rank probes its slice of the keys and stores each result into every rank's
 //      result buffer: the all-gather of hits rides on the probe kernel.
 //
 // A phase boundary is a flag per (phase, buffer, rank) in every region, raised by the last CTA
-// of the pushing kernel after a system fence, and a wait in the prologue of the consumer kernel (a
+// of the producing kernel after a system fence, and a wait in the prologue of the consumer kernel (a
 // one-warp wait kernel when several contexts share a GPU).  Two buffers alternate by epoch: a rank
 // can only start epoch e + 2 after every peer delivered e + 1, i.e. finished reading epoch e.
 // The epoch is bumped before anything can fail, statuses travel WITH the data (min-encoded words
@@ -141,72 +144,13 @@ namespace kxx {
 // consumer kernel: several contexts share one GPU and many spinning CTAs could starve the peers)
 __global__ void wait_flags_kernel(const WaitSpec W) { wait_flags_lane(W, (int)threadIdx.x); }
 
-struct XbParams {
-    Targets tg;
-    int self;         // index of my own region in tg (its slab already holds the rows: nothing to copy), -1: none
-    const uint8_t *own_slab;
-    size_t o_slab;    // my slab inside a region
-    uint32_t rows_cap, blob_cap;
-    size_t o_flag;
-    int raise_flags;
-    uint32_t epoch;
-    const uint32_t *counters;
-    uint32_t *done;
-};
-
-// Phase B: the winner rows and their names sit in this rank's own slab (the finalize wrote them
-// there); blockIdx.y picks the peer, the CTAs of that row stream rows + names into the peer's copy of
-// the slab with 16-byte stores over NVLink.  The CTA that finishes last writes the header everywhere
-// and raises the flags.
-__global__ void __launch_bounds__(256) xb_push_kernel(const XbParams P) {
-    const uint32_t n_sel = P.counters[KX_C_NSEL], blob_used = P.counters[KX_C_BLOB_CURSOR];
-    uint32_t st = 0;
-    if (P.counters[KX_C_BLOB_OVERFLOW] || n_sel > P.rows_cap || blob_used > P.blob_cap) st |= XS_SLAB_OVERFLOW;
-    const int q = (int)blockIdx.y;
-    const bool pushes = !st && q != P.self && (n_sel != 0u || blob_used != 0u);
-    if (pushes) {
-        const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-        uint8_t *dst = P.tg.region[q] + P.o_slab;
-        const size_t r16 = (size_t)n_sel * (sizeof(SlabRow) / 16);
-        const uint4 *s_rows = reinterpret_cast<const uint4 *>(P.own_slab + slab_rows_off());
-        uint4 *d_rows = reinterpret_cast<uint4 *>(dst + slab_rows_off());
-        for (size_t i = tid; i < r16; i += nth) d_rows[i] = s_rows[i];
-        const size_t b16 = ((size_t)blob_used + 15) / 16;
-        const uint4 *s_blob = reinterpret_cast<const uint4 *>(P.own_slab + slab_blob_off(P.rows_cap));
-        uint4 *d_blob = reinterpret_cast<uint4 *>(dst + slab_blob_off(P.rows_cap));
-        for (size_t i = tid; i < b16; i += nth) d_blob[i] = s_blob[i];
-    }
-    // one system fence per CTA: the barrier makes the CTA's pushes visible to thread 0, whose
-    // (cumulative) fence orders them in front of the counter and, in the last CTA, of the flags
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (pushes) __threadfence_system();
-        const uint32_t prev = atomicAdd(P.done, 1u);
-        if (prev == gridDim.x * gridDim.y - 1u) {
-            *P.done = 0u;
-            __threadfence_system();
-            SlabHeader h;
-            memset(&h, 0, sizeof h);
-            h.n_rows = st ? 0u : n_sel;
-            h.blob_bytes = st ? 0u : blob_used;
-            h.status = st;
-            h.nkeys = P.counters[KX_C_NKEYS];
-            for (int k = 0; k < P.tg.n; k++) *reinterpret_cast<SlabHeader *>(P.tg.region[k] + P.o_slab) = h;
-            __threadfence_system();
-            if (P.raise_flags)
-                for (int k = 0; k < P.tg.n; k++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[k] + P.o_flag) = P.epoch;
-        }
-    }
-}
-
 // keys a table may hold after the merge: the bound (winners + the most losers any rank keeps) is the
 // same on every rank and usually counts the winners' keys twice, so it may go well beyond the 50 %
 // load the parse is held to
 __host__ __device__ static inline uint32_t merged_key_limit(uint32_t cap) { return cap - cap / 8; }
 
 struct MergeParams {
-    const uint8_t *slabs;  // slab of rank 0; rank r at + r * stride
-    size_t stride;
+    const uint8_t *slab_of[KX_MAX_RANKS];  // rank r's slab: peer memory (read over NVLink) or the all-gathered staging copy
     int R;
     uint32_t slab_rows_cap;
     MinView mv;  // the phase-A blocks of all ranks (status words)
@@ -226,15 +170,21 @@ struct MergeParams {
 __global__ void __launch_bounds__(256) merge_kernel(const MergeParams P) {
     __shared__ uint32_t rpre[KX_MAX_RANKS + 1], bpre[KX_MAX_RANKS + 1], s_status, s_maxkeys;
     wait_flags_cta(P.wait);
+    // the R headers: one lane each (remote reads, all in flight together)
+    __shared__ uint32_t h_rows[KX_MAX_RANKS], h_blob[KX_MAX_RANKS], h_status[KX_MAX_RANKS], h_nkeys[KX_MAX_RANKS];
+    if (threadIdx.x < (unsigned)P.R) {
+        const uint4 hv = __ldcv(reinterpret_cast<const uint4 *>(P.slab_of[threadIdx.x]));  // n_rows, blob_bytes, status, nkeys
+        h_rows[threadIdx.x] = hv.x; h_blob[threadIdx.x] = hv.y; h_status[threadIdx.x] = hv.z; h_nkeys[threadIdx.x] = hv.w;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t st = min_view_status(P.mv), mk = 0, racc = 0, bacc = 0;
         for (int r = 0; r < P.R; r++) {
-            const SlabHeader *h = reinterpret_cast<const SlabHeader *>(P.slabs + (size_t)r * P.stride);
             rpre[r] = racc; bpre[r] = bacc;
-            racc += h->n_rows;
-            bacc += (h->blob_bytes + 15u) & ~15u;
-            st |= h->status;
-            const uint32_t losers = h->nkeys > h->n_rows ? h->nkeys - h->n_rows : 0u;  // local keys that are not winners
+            racc += h_rows[r];
+            bacc += (h_blob[r] + 15u) & ~15u;
+            st |= h_status[r];
+            const uint32_t losers = h_nkeys[r] > h_rows[r] ? h_nkeys[r] - h_rows[r] : 0u;  // local keys that are not winners
             mk = losers > mk ? losers : mk;
         }
         rpre[P.R] = racc; bpre[P.R] = bacc;
@@ -256,8 +206,12 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeParams P) {
     for (size_t g = tid; g < total_rows; g += nth) {
         int r = 0;
         while (r + 1 < P.R && g >= rpre[r + 1]) r++;
-        const uint8_t *slab = P.slabs + (size_t)r * P.stride;
-        const SlabRow row = reinterpret_cast<const SlabRow *>(slab + slab_rows_off())[g - rpre[r]];
+        // a 32-byte row in two uncached 16-byte loads (peer memory: never out of a stale cache line)
+        const uint4 *rp = reinterpret_cast<const uint4 *>(P.slab_of[r] + slab_rows_off()) + 2 * (size_t)(g - rpre[r]);
+        const uint4 ra = __ldcv(rp), rb = __ldcv(rp + 1);
+        SlabRow row;
+        row.key = ra.x; row.name_len = ra.y; row.line = ((unsigned long long)ra.w << 32) | ra.z;
+        row.anchor = ((unsigned long long)rb.y << 32) | rb.x; row.name_off = rb.z; row.pad = rb.w;
         P.row_key[g] = row.key; P.row_line[g] = row.line; P.row_anchor[g] = row.anchor;
         P.row_name_off[g] = bpre[r] + row.name_off; P.row_name_len[g] = row.name_len;
         const uint32_t slot = kxparse::table_claim(P.tab, row.key, nfresh);
@@ -267,8 +221,8 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeParams P) {
     for (size_t j = tid; j < total_b16; j += nth) {
         int r = 0;
         while (r + 1 < P.R && j * 16u >= bpre[r + 1]) r++;
-        const uint8_t *src = P.slabs + (size_t)r * P.stride + slab_blob_off(P.slab_rows_cap);
-        reinterpret_cast<uint4 *>(P.blob)[j] = reinterpret_cast<const uint4 *>(src)[j - bpre[r] / 16u];
+        const uint8_t *src = P.slab_of[r] + slab_blob_off(P.slab_rows_cap);
+        reinterpret_cast<uint4 *>(P.blob)[j] = __ldcv(reinterpret_cast<const uint4 *>(src) + (j - bpre[r] / 16u));
     }
 }
 
@@ -480,7 +434,7 @@ struct PhaseTrace {
     bool on = false, made = false;
     double acc[N] = {};
     int calls = 0;
-    const char *name[N] = {"trunc", "parse+resolve+xa", "waitA", "select+finalize", "xb_push", "waitB", "merge", "join", "waitC+copy", ""};
+    const char *name[N] = {"trunc", "parse+resolve+xa", "waitA", "select+finalize+tail", "-", "waitB", "merge (pull)", "join", "waitC+copy", ""};
     void init() {
         on = getenv("KXPU_TRACE_MERGE") != nullptr;
         if (on && !made) { for (auto &e : ev) cudaEventCreate(&e); made = true; }
@@ -593,19 +547,16 @@ static void shard_phase2(ShardOp &op) {
     // winners (judged against the minima over all ranks' blocks) are sanitised straight into my own slab
     const uint32_t rows_cap = op.nccl ? x->scaps.rows : x->caps.rows, blob_cap = op.nccl ? x->scaps.blob : x->caps.blob;
     uint8_t *own_slab = op.nccl ? x->send_slab : mine + L.o_slab[op.b] + (size_t)x->rank * L.slab_stride;
-    KxSlabOut so{own_slab + slab_rows_off(), rows_cap, own_slab + slab_blob_off(rows_cap), blob_cap};
+    KxSlabOut so;
+    memset(&so, 0, sizeof so);
+    so.rows = own_slab + slab_rows_off(); so.rows_cap = rows_cap; so.blob = own_slab + slab_blob_off(rows_cap); so.blob_cap = blob_cap;
+    // the last CTA of the finalize writes the slab header and tells every peer that the slab can be read
+    so.tail.on = 1; so.tail.done = x->scratch + 1; so.tail.header = reinterpret_cast<SlabHeader *>(own_slab);
+    if (!op.nccl) { so.tail.tg = targets(op); so.tail.o_flag = flag_off(1, op.b, x->rank); }
+    so.tail.epoch = op.epoch; so.tail.rows_cap = rows_cap; so.tail.blob_cap = blob_cap;
     op.rc = kx_launch_finalize(ctx, t, op.a.d_text, op.a.n, op.a.base, &mv, &ws, &so);
     if (op.rc != KXPU_OK) return;
     g_trace.mark(4, ctx->stream);
-    XbParams P;
-    memset(&P, 0, sizeof P);
-    if (op.nccl) { P.tg.n = 1; P.tg.region[0] = x->send_slab; P.o_slab = 0; P.self = 0; }
-    else { P.tg = targets(op); P.o_slab = L.o_slab[op.b] + (size_t)x->rank * L.slab_stride; P.self = x->rank; }
-    P.own_slab = own_slab; P.rows_cap = rows_cap; P.blob_cap = blob_cap;
-    P.o_flag = flag_off(1, op.b, x->rank); P.raise_flags = op.nccl ? 0 : 1; P.epoch = op.epoch;
-    P.counters = t->dev.counters; P.done = x->scratch + 1;
-    xb_push_kernel<<<dim3(op.nccl ? 1u : 64u, (unsigned)P.tg.n), 256, 0, ctx->stream>>>(P);
-    KX_LAUNCHED(ctx);
     g_trace.mark(5, ctx->stream);
 }
 
@@ -633,7 +584,9 @@ static void shard_phase3(ShardOp &op) {
     MergeParams M;
     memset(&M, 0, sizeof M);
     M.wait = ws;
-    M.slabs = mine + L.o_slab[op.b]; M.stride = L.slab_stride; M.R = x->nranks;
+    M.R = x->nranks;
+    for (int r = 0; r < x->nranks; r++)  // rank r's slab sits in ITS region (peer memory); NCCL: in my staging copy
+        M.slab_of[r] = (op.nccl ? mine : x->peer[r]) + L.o_slab[op.b] + (size_t)r * L.slab_stride;
     M.slab_rows_cap = op.nccl ? x->scaps.rows : x->caps.rows;
     M.mv = MinView{reinterpret_cast<const unsigned long long *>(mine + L.o_a[op.b]), L.a_stride / 8, x->nranks, nullptr};
     M.tab = t->dev; M.row_key = t->row_key; M.row_name_off = t->row_name_off; M.row_name_len = t->row_name_len;

@@ -66,6 +66,19 @@ struct Targets {  // where a push goes: every rank's region (peer memory) or thi
     int n;
 };
 
+// Phase B is a PULL: the finalize writes the winners into this rank's own slab; its last CTA adds the header and
+// raises "slab ready" on every peer; a peer's merge kernel reads the slab over NVLink.  (A push kernel in
+// between cost 11-18 us per load for the launch, one system fence per CTA and two in the last one.)
+struct SlabTail {
+    int on;
+    uint32_t *done;          // last-CTA counter
+    SlabHeader *header;      // of my own slab (local memory)
+    Targets tg;              // regions that hold the flags (peer transport), n = 0: no flags (NCCL transport)
+    size_t o_flag;
+    uint32_t epoch;
+    uint32_t rows_cap, blob_cap;
+};
+
 struct XaParams {
     Targets tg;
     size_t o_a;     // my phase-A block inside a region

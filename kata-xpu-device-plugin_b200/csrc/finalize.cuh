@@ -118,6 +118,7 @@ struct FinalizeParams {
     kxx::SlabRow *slab_rows;  // sharded load: rows go here (this rank's slab, 32-byte records) instead of the row arrays
     uint32_t slab_rows_cap;
     uint32_t scan_w;          // table slots a warp scans per step: 8 (latency) or 32 (big tables)
+    kxx::SlabTail tail;       // sharded load: header + "slab ready" flags by the last CTA
     long long *trace;         // debug (KXPU_TRACE_SMALL): [gridDim.x][8] clock64 of thread 0 inside the first step
 };
 
@@ -439,6 +440,31 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, co
 __global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const FinalizeParams F) {
     kxx::wait_flags_cta(F.wait);
     select_finalize_body(F, F.scan_w);
+    if (F.tail.on) {
+        // one fence per CTA: the barrier makes the CTA's rows visible to thread 0, whose (cumulative) fence orders them
+        // in front of the counter and, in the last CTA, of the header and the flags
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const uint32_t prev = atomicAdd(F.tail.done, 1u);
+            if (prev == gridDim.x - 1u) {
+                *F.tail.done = 0u;
+                __threadfence();
+                const volatile uint32_t *c = F.tab.counters;
+                const uint32_t n_sel = c[KX_C_NSEL], blob_used = c[KX_C_BLOB_CURSOR];
+                const bool over = c[KX_C_BLOB_OVERFLOW] || n_sel > F.tail.rows_cap || blob_used > F.tail.blob_cap;
+                kxx::SlabHeader h;
+                memset(&h, 0, sizeof h);
+                h.n_rows = over ? 0u : n_sel;
+                h.blob_bytes = over ? 0u : blob_used;
+                h.status = over ? kxx::XS_SLAB_OVERFLOW : 0u;
+                h.nkeys = c[KX_C_NKEYS];
+                *F.tail.header = h;
+                __threadfence_system();
+                for (int k = 0; k < F.tail.tg.n; k++) *reinterpret_cast<volatile uint32_t *>(F.tail.tg.region[k] + F.tail.o_flag) = F.tail.epoch;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------

@@ -48,6 +48,7 @@ struct KxSlabOut {
     uint32_t rows_cap;
     uint8_t *blob;
     uint32_t blob_cap;
+    kxx::SlabTail tail;  // header + flags by the last CTA of the finalize
 };
 // mv (may be null: the table's own minima): what validity is judged against
 int32_t kx_launch_finalize(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, size_t n, unsigned long long base,
