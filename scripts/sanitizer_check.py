@@ -18,6 +18,16 @@ devs = W.cfg5_devices(3000)
 print("classify", res["n_accepted"], "json", len(kx.cdi_emit(1, devs)), "yaml", len(kx.cdi_emit(0, devs)))
 print("alloc", len(kx.alloc_names(devs["index"])[0]), "lw", len(kx.lw_encode(res["group_ids"][:100])))
 tab.free()
+# zero-copy join: text, keys and rows in mapped pinned host memory
+h_t, p1 = kx.pinned(len(text)); h_t[:] = np.frombuffer(text, np.uint8)
+qq = W.cfg2_queries(keys)
+h_q, p2 = kx.pinned(len(qq) * 4, np.uint32); h_q[:] = qq
+h_r, p3 = kx.pinned(len(qq) * 4, np.int32)
+tz, rz = kx.pciids_join(h_t, h_q, rows_out=h_r)
+print("zero-copy join rows", tz.rows, "hits", int((rz >= 0).sum()))
+tz.free()
+for p in (p1, p2, p3):
+    kx.pinned_free(p)
 # sharded load + join, three contexts of one process on this GPU
 m = K.KxpuMulti([0, 0, 0])
 big = text * 2
