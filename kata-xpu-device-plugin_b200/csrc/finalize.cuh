@@ -302,6 +302,7 @@ __device__ __forceinline__ void select_finalize_body(const FinalizeParams &F, co
             if (lane >= r0 && lane < r0 + 4u && lane < nvalid) my_len = gtot;
             for (uint32_t g = 0; g < 4u; g++)
                 if ((gslow >> (8u * g)) & 1u) slow_m |= 1u << (r0 + g);
+            __syncwarp();  // the next round overwrites the raw windows this round's lanes read from
         }
         __syncwarp();
         SF_MARK(1);
