@@ -7,8 +7,9 @@ One step = parse the text into the (vendor,device) table and join the 2^20 keys 
   N = 1   one kxpu_pciids_join_device call (parse + resolve + finalize + join, one host round trip);
   N > 1   STRONG scaling (default): the SAME 1.458 GB text is cut into N shards at vendor lines
           (kxpu_plan_shards), the SAME 2^20 keys into N slices; one kxpu_pciids_join_sharded call per
-          step: parse the shard, all-reduce(min) of the first anchors and push of the winning rows over
-          NVSwitch peer memory, insert, probe the key slice with the hits stored into every rank.
+          step: parse the shard, all-reduce(min) of the first anchors over NVSwitch peer memory, winners
+          published per rank and pulled + inserted by every rank, probe of the key slice with the hits
+          stored into every rank.
           A WEAK-scaling measurement (every rank its own x1000 shard of one logical x(1000*N) text and
           its own 2^20 keys) rides in the same line under "weak_scaling" (--scaling weak makes it the
           headline instead).
@@ -21,6 +22,10 @@ One step = parse the text into the (vendor,device) table and join the 2^20 keys 
   parity     outside the timed region every rank's table and join result are compared with the
              oracle's table of the whole text (kxo_table_build on the 1.458 GB buffer, rank 0) and
              with each other ("parity_checked").
+  aux        the other rows of the hot path, each with its own roofline: cfg2 (the real 1.4 MB pci.ids once +
+             1024 keys: device time with inputs in HBM, and wall clock of ONE kxpu_pciids_join call on pinned
+             host buffers -- zero-copy ingest, no cudaMemcpy), cfg3 classify, cfg5 CDI emit (JSON / YAML).
+  cpu_best   the honest CPU comparator: single-pass build + binary-search join on 1 / physical / all threads.
   --impl reference   the reference's own algorithm (getDeviceName: one linear rescan of the
              text per key, pkg/device_plugin/device_plugin.go:208-275) restated in C
              (oracle/, Go toolchain absent), all host threads, bounded sample per step.
