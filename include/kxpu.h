@@ -96,6 +96,8 @@ int32_t kxpu_dev_download(kxpu_ctx *ctx, void *h_dst, const void *d_src, size_t 
 /* d_dst[i*n .. (i+1)*n) = d_src[0..n) for i in [0,copies): builds the "pci.ids x1000"
  * text of BASELINE.json configs[3] on the device. */
 int32_t kxpu_dev_replicate(kxpu_ctx *ctx, void *d_dst, const void *d_src, size_t n, size_t copies);
+/* page-locked host memory the GPU can address (cudaMallocHost): fast H2D source, zero-copy input of
+ * kxpu_pciids_join */
 int32_t kxpu_pinned_alloc(kxpu_ctx *ctx, size_t bytes, void **h_out);
 int32_t kxpu_pinned_free(kxpu_ctx *ctx, void *h_ptr);
 int32_t kxpu_sync(kxpu_ctx *ctx);
@@ -144,7 +146,13 @@ int32_t kxpu_pciids_join_device(kxpu_ctx *ctx, const void *d_text, size_t n, con
 /* The same from host buffers: text and keys are copied to the GPU, the row handles come back in
  * rows_out, ONE host round trip.  This is the start-up path of the plugin: createDevicePlugins needs
  * the name of every device id once (device_plugin.go:91-105).  A small text (the real pci.ids is
- * 1.4 MB) is parsed, folded, finalized and joined by one cooperative kernel launch. */
+ * 1.4 MB) is parsed, folded, finalized and joined by one cooperative kernel launch.
+ * Zero-copy: when text, keys AND rows_out lie in pinned host memory the GPU can address
+ * (kxpu_pinned_alloc, cudaHostAlloc, cudaHostRegister) and the text is 16-byte aligned, nothing is
+ * copied: that kernel pulls the text over PCIe itself and writes the row handles to rows_out; the
+ * call is one launch and one stream synchronisation.  Pageable buffers take the copying path with
+ * the same results.  (A Go host reads the file into a kxpu_pinned_alloc buffer instead of
+ * os.ReadFile's Go slice: C memory, nothing to pin for cgo.) */
 int32_t kxpu_pciids_join(kxpu_ctx *ctx, const uint8_t *text, size_t n, const uint32_t *keys, size_t nq,
                          int32_t *rows_out, kxpu_table **out);
 
