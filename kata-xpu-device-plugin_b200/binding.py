@@ -256,6 +256,25 @@ class Kxpu:
                                           C.byref(h)))
         return Table(self, h), rows
 
+    def pciids_join_call(self, text, keys, rows_out):
+        """The bare kxpu_pciids_join C call with its arguments prepared once (numpy arrays that stay alive): returns
+        a function that runs the call and hands back the table handle -- what a C / cgo host executes, without the
+        ~7 us of numpy / ctypes argument marshalling per call."""
+        fn, ctx = self.L.kxpu_pciids_join, self.ctx
+        p_text, n_text = C.c_void_p(text.ctypes.data), C.c_size_t(text.size)
+        p_keys, n_keys, p_rows = _ptr(keys), C.c_size_t(len(keys)), _ptr(rows_out)
+
+        def call():
+            h = C.c_void_p()
+            rc = fn(ctx, p_text, n_text, p_keys, n_keys, p_rows, C.byref(h))
+            if rc != 0:
+                self._chk(rc)
+            return h
+        return call
+
+    def table_free_handle(self, h):
+        self._chk(self.L.kxpu_table_free(self.ctx, h))
+
     def pciids_load_sharded(self, d_text, n, global_base):
         h = C.c_void_p()
         self._chk(self.L.kxpu_pciids_load_sharded(self.ctx, d_text, n, global_base, C.byref(h)))
