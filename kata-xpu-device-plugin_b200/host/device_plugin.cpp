@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cerrno>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -398,18 +399,55 @@ Error Plugin::createIommuDeviceMap() {
     return Error();
 }
 
-Error Plugin::ensureTable() {
-    if (table_) return Error();
+// The pci.ids file into page-locked memory the GPU can address (kxpu_pinned_alloc): with text, keys and rows in
+// such buffers kxpu_pciids_join copies nothing -- one cooperative kernel pulls the text over PCIe, builds the
+// table and writes the row handles back (include/kxpu.h).  Falls back to ordinary memory when pinning fails.
+namespace {
+struct PinnedBuf {
+    kxpu_ctx *ctx;
+    void *p = nullptr;
+    bool pinned = false;
+    size_t n = 0;
+    PinnedBuf(kxpu_ctx *c, size_t bytes) : ctx(c), n(bytes) {
+        if (kxpu_pinned_alloc(ctx, bytes ? bytes : 16, &p) == KXPU_OK && p) pinned = true;
+        else p = malloc(bytes ? bytes : 16);
+    }
+    ~PinnedBuf() {
+        if (pinned) kxpu_pinned_free(ctx, p);
+        else free(p);
+    }
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+};
+}  // namespace
+
+// First use: ONE kxpu_pciids_join call reads the file (device_plugin.go:210), builds the table and joins `keys`
+// (the start-up batch of createDevicePlugins, device_plugin.go:91-105).  keys may be empty (load only).
+Error Plugin::loadAndJoin(const std::vector<uint32_t> &keys, std::vector<int32_t> &rows) {
     FILE *f = fopen(pciIdsFilePath.c_str(), "rb");  // device_plugin.go:210
     if (!f) return fail("Error opening pci ids file " + pciIdsFilePath);
-    std::vector<uint8_t> text;
-    uint8_t buf[1 << 16];
-    size_t k;
-    while ((k = fread(buf, 1, sizeof buf, f)) > 0) text.insert(text.end(), buf, buf + k);
+    std::vector<uint8_t> head;
+    size_t n = 0;
+    if (fseek(f, 0, SEEK_END) == 0) {
+        const long sz = ftell(f);
+        if (sz > 0) n = (size_t)sz;
+        rewind(f);
+    }
+    PinnedBuf text(ctx_, n), hk(ctx_, keys.size() * 4), hr(ctx_, keys.size() * 4);
+    if (!text.p || !hk.p || !hr.p) { fclose(f); return fail("out of memory reading " + pciIdsFilePath); }
+    const size_t got = n ? fread(text.p, 1, n, f) : 0;
     fclose(f);
-    int32_t rc = kxpu_pciids_load(ctx_, text.data(), text.size(), &table_);
-    if (rc != KXPU_OK) { table_ = nullptr; return kxfail(ctx_, "kxpu_pciids_load", rc); }
+    if (!keys.empty()) memcpy(hk.p, keys.data(), keys.size() * 4);
+    const int32_t rc = kxpu_pciids_join(ctx_, (const uint8_t *)text.p, got, (const uint32_t *)hk.p, keys.size(), (int32_t *)hr.p, &table_);
+    if (rc != KXPU_OK) { table_ = nullptr; return kxfail(ctx_, "kxpu_pciids_join", rc); }
+    rows.assign((const int32_t *)hr.p, (const int32_t *)hr.p + keys.size());
     return Error();
+}
+
+Error Plugin::ensureTable() {
+    if (table_) return Error();
+    std::vector<int32_t> none;
+    return loadAndJoin({}, none);
 }
 
 static bool parseHex4(const std::string &s, uint32_t &v) {
@@ -430,17 +468,22 @@ static bool parseHex4(const std::string &s, uint32_t &v) {
 // reference; sysfs ids are four lowercase hex digits, anything else is treated as not found.
 std::vector<std::string> Plugin::getDeviceNames(const std::vector<std::string> &deviceIDs) {
     std::vector<std::string> out(deviceIDs.size());
-    Error e = ensureTable();
-    if (e) { fprintf(stderr, "%s\n", e.message.c_str()); return out; }  // :211-214
     std::vector<uint32_t> keys;
     std::vector<size_t> where;
     for (size_t i = 0; i < deviceIDs.size(); i++) {
         uint32_t d;
         if (parseHex4(deviceIDs[i], d)) { keys.push_back((0x10deu << 16) | d); where.push_back(i); }  // nvidiaVendorID, :19
     }
-    if (keys.empty()) return out;
     std::vector<int32_t> rows(keys.size(), KXPU_ROW_MISS);
-    if (kxpu_lookup(ctx_, table_, keys.data(), keys.size(), rows.data()) != KXPU_OK) return out;
+    if (!table_) {
+        // start-up: file -> table -> row handles of the whole batch in one call
+        Error e = loadAndJoin(keys, rows);
+        if (e) { fprintf(stderr, "%s\n", e.message.c_str()); return out; }  // :211-214
+        if (keys.empty()) return out;
+    } else {
+        if (keys.empty()) return out;
+        if (kxpu_lookup(ctx_, table_, keys.data(), keys.size(), rows.data()) != KXPU_OK) return out;
+    }
     std::vector<uint32_t> offs(keys.size() + 1);
     size_t need = 0;
     int32_t rc = kxpu_names(ctx_, table_, rows.data(), rows.size(), nullptr, 0, offs.data(), &need);

@@ -168,6 +168,8 @@ class Plugin {
     kxpu_ctx *ctx_;
     kxpu_table *table_ = nullptr;
     Error ensureTable();
+    // first use: kxpu_pciids_join on pinned buffers = file -> table -> row handles of `keys` in one call
+    Error loadAndJoin(const std::vector<uint32_t> &keys, std::vector<int32_t> &rows);
     BindWatcher bindWatcher_;
     bool haveSnapshotGen_ = false;
     uint64_t snapshotGen_ = 0;
