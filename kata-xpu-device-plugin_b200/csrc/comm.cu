@@ -280,11 +280,11 @@ __global__ void __launch_bounds__(256) join_gather_kernel(const JoinParams P) {
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        kx_fence_sys();
         const uint32_t prev = atomicAdd(P.done, 1u);
         if (prev == gridDim.x - 1u) {
             *P.done = 0u;
-            __threadfence_system();
+            kx_fence_sys();
             if (P.raise_flags)
                 for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[q] + P.o_flag) = P.epoch;
         }

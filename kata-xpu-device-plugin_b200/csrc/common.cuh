@@ -113,5 +113,12 @@ struct KxScratch {
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t kx_lane() { return threadIdx.x & 31u; }
 
+// Release / acquire fences.  __threadfence() and __threadfence_system() are fence.sc (MEMBAR.SC): sequentially
+// consistent, i.e. totally ordered against every other SC fence in flight -- with one per CTA at a phase
+// boundary they queue up.  Every fence in this library orders data in front of a flag / counter (release) or a
+// flag / counter in front of data (acquire): fence.acq_rel (MEMBAR.ALL + L1 invalidate) is what that needs.
+__device__ __forceinline__ void kx_fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void kx_fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t kx_hash(uint32_t key) { return key * 0x9E3779B1u; }
 #endif

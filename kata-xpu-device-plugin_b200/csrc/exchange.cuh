@@ -114,7 +114,7 @@ __device__ __forceinline__ void xa_finish(const XaParams &P) {
         a[A_TRUNC] = t;
         a[A_STATUS] = st;
     }
-    __threadfence_system();
+    kx_fence_sys();
     if (P.raise_flags)
         for (int q = 0; q < P.tg.n; q++) *reinterpret_cast<volatile uint32_t *>(P.tg.region[q] + P.o_flag) = P.epoch;
 }
@@ -134,7 +134,7 @@ __device__ __forceinline__ void wait_flags_lane(const WaitSpec &W, int q) {
             if (clock64() - t0 > 8000000000ll) { *W.timeout_flag = 1u; break; }  // a peer died or the ranks lost step
         }
     }
-    __threadfence_system();
+    kx_fence_sys();
 }
 // prologue of a consumer kernel (every CTA): the first warp waits, the barrier releases the others
 __device__ __forceinline__ void wait_flags_cta(const WaitSpec &W) {

@@ -446,11 +446,11 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const
         // in front of the counter and, in the last CTA, of the header and the flags
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence_system();
+            kx_fence_sys();
             const uint32_t prev = atomicAdd(F.tail.done, 1u);
             if (prev == gridDim.x - 1u) {
                 *F.tail.done = 0u;
-                __threadfence();
+                kx_fence_gpu();
                 const volatile uint32_t *c = F.tab.counters;
                 const uint32_t n_sel = c[KX_C_NSEL], blob_used = c[KX_C_BLOB_CURSOR];
                 const bool over = c[KX_C_BLOB_OVERFLOW] || n_sel > F.tail.rows_cap || blob_used > F.tail.blob_cap;
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const
                 h.status = over ? kxx::XS_SLAB_OVERFLOW : 0u;
                 h.nkeys = c[KX_C_NKEYS];
                 *F.tail.header = h;
-                __threadfence_system();
+                kx_fence_sys();
                 for (int k = 0; k < F.tail.tg.n; k++) *reinterpret_cast<volatile uint32_t *>(F.tail.tg.region[k] + F.tail.o_flag) = F.tail.epoch;
             }
         }

@@ -529,11 +529,11 @@ __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Pa
         kxx::xa_push_slice(P.xa, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence_system();
+            kx_fence_sys();
             const uint32_t prev = atomicAdd(P.xa_done, 1u);
             if (prev == gridDim.x - 1u) {
                 *P.xa_done = 0u;
-                __threadfence_system();
+                kx_fence_sys();
                 kxx::xa_finish(P.xa);
             }
         }

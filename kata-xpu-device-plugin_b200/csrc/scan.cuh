@@ -63,7 +63,7 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long *state
     const unsigned long long tag = (unsigned long long)(epoch & 0xffffffu) << ST_EPOCH_SHIFT;
     if (lane == 0) {
         *reinterpret_cast<volatile unsigned long long *>(&state[tile]) = tag | (tile == 0 ? ST_PFX : ST_AGG) | (aggregate & ST_VAL);
-        __threadfence();
+        kx_fence_gpu();
     }
     unsigned long long excl = 0;
     long long j0 = (long long)tile - 1;  // lane 0 looks at j0, lane 1 at j0 - 1, ...
@@ -91,7 +91,7 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long *state
     }
     if (lane == 0 && tile != 0) {
         *reinterpret_cast<volatile unsigned long long *>(&state[tile]) = tag | ST_PFX | ((excl + aggregate) & ST_VAL);
-        __threadfence();
+        kx_fence_gpu();
     }
     return excl;
 }

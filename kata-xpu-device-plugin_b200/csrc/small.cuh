@@ -39,11 +39,11 @@ struct SmallParams {
 __device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        kx_fence_gpu();
         atomicAdd(ctr, 1u);
         while (*reinterpret_cast<volatile uint32_t *>(ctr) < target) {
         }
-        __threadfence();
+        kx_fence_gpu();
     }
     __syncthreads();
 }
