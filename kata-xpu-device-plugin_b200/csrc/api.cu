@@ -369,7 +369,8 @@ int32_t kx_launch_parse(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, siz
     if (num_chunks == 0) {
         if (xa) {  // an empty shard still takes part in the exchange
             P.tab = t->dev;
-            kxparse5::resolve_chunks_kernel<<<1, kxparse5::RES_WARPS * 32, 0, ctx->stream>>>(P);
+            P.task_ctas = 0;
+            kxparse5::resolve_chunks_kernel<<<kxparse5::XA_CTAS, kxparse5::RES_WARPS * 32, 0, ctx->stream>>>(P);
             KX_LAUNCHED(ctx);
             KX_CUDA(ctx, cudaGetLastError());
         }
@@ -409,7 +410,8 @@ int32_t kx_launch_parse(kxpu_ctx *ctx, kxpu_table *t, const uint8_t *d_text, siz
         kxparse5::resolve_ranges_kernel<<<(P.num_ranges + 255u) / 256u, 256, 0, ctx->stream>>>(P);
         KX_LAUNCHED(ctx);
         const uint32_t rgrid = std::min<uint32_t>(4u * ctx->sm_count, (num_chunks + kxparse5::RES_WARPS - 1) / kxparse5::RES_WARPS);
-        kxparse5::resolve_chunks_kernel<<<rgrid, kxparse5::RES_WARPS * 32, 0, ctx->stream>>>(P);
+        P.task_ctas = rgrid;
+        kxparse5::resolve_chunks_kernel<<<rgrid + (xa ? kxparse5::XA_CTAS : 0u), kxparse5::RES_WARPS * 32, 0, ctx->stream>>>(P);
         KX_LAUNCHED(ctx);
     }
     KX_CUDA(ctx, cudaGetLastError());

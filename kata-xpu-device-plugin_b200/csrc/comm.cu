@@ -7,7 +7,9 @@
 // (device_plugin.go:263-267) is then decided across shards in two exchange phases:
 //
 //   A  all-reduce(min) of vendor_first (+ the bufio.ErrTooLong cut-off and status bits), done as an
-//      all-gather with the min taken by the reader: every rank stores its dense first-anchor array
+//      all-gather with the min taken by the reader (pushed by extra CTAs of resolve_chunks_kernel while the others
+//      fold -- vendor_first is final since the parse kernel): every rank stores
+//      its dense first-anchor array
 //      (512 KB, plain 16-byte stores over NVLink -- remote 64-bit atomics cost ~10 ns apiece, the
 //      copy is one streaming write) into ITS block of every rank's exchange region; nothing is ever
 //      cleared, the block is overwritten whole each epoch.  After phase A every rank knows the
@@ -505,7 +507,7 @@ static void shard_phase1(ShardOp &op) {
     if (op.have_trunc) op.rc = kx_launch_trunc(ctx, t, op.a.d_text, op.a.n, op.a.base);
     if (op.rc != KXPU_OK) return;
     g_trace.mark(1, ctx->stream);
-    // parse + resolve; the last CTA of the resolve kernel pushes the shard's minima (phase A)
+    // parse + resolve; extra CTAs of resolve_chunks_kernel push the shard's minima (phase A)
     const XLayout &L = layout(op);
     KxXaHook hook;
     memset(&hook, 0, sizeof hook);

@@ -459,6 +459,9 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 8) select_finalize_kernel(const
                 h.n_rows = over ? 0u : n_sel;
                 h.blob_bytes = over ? 0u : blob_used;
                 h.status = over ? kxx::XS_SLAB_OVERFLOW : 0u;
+                // phase A left before the resolve pass: what that pass found out about the table travels here
+                if (c[KX_C_OVERFLOW]) h.status |= kxx::XS_GROW | kxx::XS_FULL;
+                if (c[KX_C_NKEYS] > F.tab.max_keys) h.status |= kxx::XS_GROW;
                 h.nkeys = c[KX_C_NKEYS];
                 *F.tail.header = h;
                 kx_fence_sys();

@@ -53,7 +53,9 @@ struct Params5 {
     uint32_t *tasks;                  // [num_chunks] resolve: chunks to stage again, count in counters[KX_C_DEFER]
     KxTableDev tab;
     unsigned long long carry_in;
-    // sharded load: the CTA of the last resolve kernel that finishes last pushes this shard's minima (phase A)
+    // sharded load, phase A: vendor_first is final when the parse kernel is through, so the push of this shard's minima
+    // rides on resolve_chunks_kernel as extra CTAs (behind the task_ctas that fold) and runs while those fold
+    uint32_t task_ctas;
     int xa_on;
     uint32_t *xa_done;
     kxx::XaParams xa;
@@ -380,6 +382,8 @@ __global__ void __launch_bounds__(NT, 4) parse_kernel_v5(const Params5 P) {
 // backwards 32 at a time -- one step for real data, at most num_ranges/32 steps for a text whose
 // top-level lines are megabytes apart.  The governing line is dead for all but the first copy of
 // a vendor block; only then the range's leading chunks are queued for step 2.
+constexpr uint32_t XA_CTAS = 64;  // extra CTAs of resolve_chunks_kernel that push phase A
+
 __global__ void __launch_bounds__(256) resolve_ranges_kernel(const Params5 P) {
     const uint32_t rr = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
@@ -438,6 +442,24 @@ __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Pa
     __shared__ __align__(16) uint8_t stg[RES_WARPS][STG_BYTES];
     __shared__ __align__(8) unsigned long long bars[RES_WARPS];
     __shared__ uint16_t plist[RES_WARPS][704];  // a 2 KiB chunk holds at most 683 candidate lines ("\tX\n")
+    if (blockIdx.x >= P.task_ctas) {
+        // phase A of the sharded load: these CTAs push slices of the shard's vendor minima into every rank's region while
+        // the others fold; the one that finishes last adds cut-off and status and raises the flags (the barrier +
+        // thread 0's cumulative system fence order each CTA's pushes in front of its count).  What the folds may
+        // still find out (table full) travels with phase B.
+        kxx::xa_push_slice(P.xa, (blockIdx.x - P.task_ctas) * blockDim.x + threadIdx.x, XA_CTAS * blockDim.x);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            kx_fence_sys();
+            const uint32_t prev = atomicAdd(P.xa_done, 1u);
+            if (prev == XA_CTAS - 1u) {
+                *P.xa_done = 0u;
+                kx_fence_sys();
+                kxx::xa_finish(P.xa);
+            }
+        }
+        return;
+    }
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t k7f = 0x7f7f7f7fu, k0a = 0x0a0a0a0au, k80 = 0x80808080u;
@@ -453,7 +475,7 @@ __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Pa
     uint32_t par = 0, nfresh = 0;
     const bool small_tab = P.tab.cap <= (1u << 20);
     uint32_t it = 0;
-    for (uint32_t t = blockIdx.x * RES_WARPS + w; t < n_tasks; t += gridDim.x * RES_WARPS, it++) {
+    for (uint32_t t = blockIdx.x * RES_WARPS + w; t < n_tasks; t += P.task_ctas * RES_WARPS, it++) {
         // table full: the host grows it and parses again (polled every fourth task: a stale answer costs bounded probing)
         if ((it & 3u) == 0u && *reinterpret_cast<volatile uint32_t *>(&P.tab.counters[KX_C_OVERFLOW]) != 0u) break;
         const uint32_t gg = P.tasks[t];
@@ -520,23 +542,6 @@ __global__ void __launch_bounds__(RES_WARPS * 32) resolve_chunks_kernel(const Pa
         }
         __syncwarp();
         flush_fresh(P.tab, nfresh);
-    }
-    if (P.xa_on) {
-        // phase A of the sharded load rides on this kernel: every CTA pushes its slice of the shard's
-        // vendor minima; the table is final once every CTA is through, the last one adds cut-off and
-        // status and raises the flags (the barrier + thread 0's cumulative system fence order each
-        // CTA's pushes in front of its count)
-        kxx::xa_push_slice(P.xa, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            kx_fence_sys();
-            const uint32_t prev = atomicAdd(P.xa_done, 1u);
-            if (prev == gridDim.x - 1u) {
-                *P.xa_done = 0u;
-                kx_fence_sys();
-                kxx::xa_finish(P.xa);
-            }
-        }
     }
 }
 
